@@ -1,0 +1,60 @@
+"""2-hop candidate enumeration (K6) — the GPU replacement for /root/reference/filter.py:96-109.
+
+``two_hop(adj)`` returns the reference's ``all_edges`` as int32 ``[2, N]`` on the device, in the
+reference's column-major order (sorted by (all_edges[1], all_edges[0])).  ``owner_counts`` /
+``two_hop(adj, v_lo, v_hi)`` work on a contiguous owner range so callers can stream slabs of a
+graph whose full candidate list would not fit (ogbl-ppa scale) or shard owners across GPUs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import EpsError, check
+from .graph import SparseAdj
+from .ops import _need_cuda, _ptr, _stream, _ws
+
+
+def owner_counts(adj: SparseAdj, v_lo: int = 0, v_hi: int | None = None) -> torch.Tensor:
+    """#candidates of every owner v in [v_lo, v_hi) as int64."""
+    _need_cuda(adj.col)
+    lib = _lib.load()
+    v_hi = adj.n if v_hi is None else v_hi
+    counts = torch.zeros(max(v_hi - v_lo, 0), dtype=torch.int32, device=adj.device)
+    ws = _ws(lib.eps_twohop_workspace_bytes(), adj.device)
+    check(lib.eps_twohop_candidates(_ptr(adj.rowptr), _ptr(adj.col), adj.n, v_lo, v_hi, None, _ptr(counts),
+                                    None, None, _ptr(ws), ws.numel(), _stream()), "eps_twohop_candidates")
+    return counts.long() & 0xFFFFFFFF
+
+
+def two_hop(adj: SparseAdj, v_lo: int = 0, v_hi: int | None = None, counts: torch.Tensor | None = None):
+    """(u, v) candidate list of owners [v_lo, v_hi): int32 [2, N], column-major reference order."""
+    _need_cuda(adj.col)
+    lib = _lib.load()
+    v_hi = adj.n if v_hi is None else v_hi
+    if counts is None:
+        counts = owner_counts(adj, v_lo, v_hi)
+    offsets = torch.zeros(counts.numel() + 1, dtype=torch.int64, device=adj.device)
+    torch.cumsum(counts, 0, out=offsets[1:])
+    N = int(offsets[-1].item())
+    if N >= 2**31:
+        raise EpsError(f"{N} candidates in one slab; split the owner range (see filter_step.iter_slabs)")
+    edges = torch.empty((2, N), dtype=torch.int32, device=adj.device)
+    if N == 0:
+        return edges
+    ws = _ws(lib.eps_twohop_workspace_bytes(), adj.device)
+    check(lib.eps_twohop_candidates(_ptr(adj.rowptr), _ptr(adj.col), adj.n, v_lo, v_hi, _ptr(offsets), None,
+                                    _ptr(edges[0]), _ptr(edges[1]), _ptr(ws), ws.numel(), _stream()),
+          "eps_twohop_candidates")
+    return edges
+
+
+def two_path_work(adj: SparseAdj) -> torch.Tensor:
+    """Per-owner work estimate sum_{k in N(v)} deg(k) (the 2-path count), used to cut owner ranges
+    into equal-work slabs / GPU shards.  Torch ops only; device-agnostic."""
+    deg = adj.degree().long()
+    contrib = deg[adj.col.long()]
+    out = torch.zeros(adj.n, dtype=torch.int64, device=adj.device)
+    return out.index_add_(0, adj.row(), contrib)

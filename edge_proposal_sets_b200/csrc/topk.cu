@@ -1,0 +1,401 @@
+// K4 — top-k proposal selection: radix select + ordered compaction + stable LSD sort.
+//
+// Replaces /root/reference/filter.py:160-161 (full CPU sort of all N candidate scores) for the
+// only part rank.py ever reads, the first k rows (/root/reference/rank.py:294).
+//
+// Order contract: score descending, ties by position ascending — exactly
+// torch.sort(descending=True, stable=True).  Achieved without a 64-bit composite key:
+//   1. map score -> uint32 key, ascending key == descending score (-0.0 folded into +0.0);
+//   2. three histogram passes (11+11+10 bits) find T = the k-th smallest key and
+//      less = #{key < T}; r = k - less elements equal to T are still needed;
+//   3. an ORDERED compaction (per-tile counts -> scan -> write) emits, in position order, every
+//      element with key < T and the first r elements with key == T;
+//   4. a STABLE 4x8-bit LSD radix sort by key alone keeps equal keys in position order.
+// All kernels are HBM streaming passes over `score` (5 reads of 4*M bytes) or over the k
+// survivors; the algorithmic figure is a single 4*M read + 12*k out.
+#include "eps_common.cuh"
+
+namespace eps {
+
+constexpr int TK_THREADS = 256;
+constexpr int TK_TILE = 4096;      // elements per block in count / write kernels
+constexpr int SORT_TILE = 2048;    // elements per block in the LSD sort
+
+struct TopkState {
+  uint32_t prefix;      // bits of T found so far
+  uint32_t k_rem;       // rank still to resolve inside the current bucket (1-based)
+  uint32_t less_total;  // #{key < prefix-bucket}
+  uint32_t need_eq;     // r, written after the last pass
+};
+
+__device__ __forceinline__ uint32_t score_key(float s) {
+  uint32_t b = __float_as_uint(s + 0.0f);               // -0.0 -> +0.0
+  uint32_t asc = b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);  // ascending float order
+  return ~asc;                                          // ascending key == descending score
+}
+
+template <int PASS>
+__device__ __forceinline__ bool pass_match(uint32_t key, uint32_t prefix) {
+  if (PASS == 0) return true;
+  if (PASS == 1) return (key >> 21) == (prefix >> 21);
+  return (key >> 10) == (prefix >> 10);
+}
+template <int PASS>
+__device__ __forceinline__ uint32_t pass_digit(uint32_t key) {
+  if (PASS == 0) return key >> 21;
+  if (PASS == 1) return (key >> 10) & 0x7ffu;
+  return key & 0x3ffu;
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(TK_THREADS)
+topk_hist_kernel(const float *__restrict__ score, long long M, const TopkState *state,
+                 uint32_t *__restrict__ hist /*[2048]*/) {
+  __shared__ uint32_t sh[2048];
+  for (int i = threadIdx.x; i < 2048; i += TK_THREADS) sh[i] = 0;
+  __syncthreads();
+  const uint32_t prefix = PASS ? state->prefix : 0;
+  const int lane = lane_id();
+  const long long stride = (long long)gridDim.x * TK_THREADS;
+  // whole warps iterate together so the match/ballot below is convergent
+  const long long start = (long long)blockIdx.x * TK_THREADS + threadIdx.x;
+  const long long mround = ((M + 31) / 32) * 32;
+  for (long long i = start; i - lane < mround && (i - lane) < M; i += stride) {
+    const bool in = i < M;
+    uint32_t key = in ? score_key(score[i]) : 0;
+    const bool ok = in && pass_match<PASS>(key, prefix);
+    // lanes that do not take part get unique ids so they match nobody
+    const uint32_t d = ok ? pass_digit<PASS>(key) : (0x10000u | lane);
+    const unsigned peers = __match_any_sync(FULL, d);
+    if (ok && lane == (__ffs(peers) - 1)) atomicAdd(&sh[d], (uint32_t)__popc(peers));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2048; i += TK_THREADS)
+    if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+template <int PASS>
+__global__ void topk_pick_kernel(TopkState *state, const uint32_t *hist, uint32_t k) {
+  if (threadIdx.x != 0) return;
+  const int nb = (PASS == 2) ? 1024 : 2048;
+  const int shift = (PASS == 0) ? 21 : (PASS == 1 ? 10 : 0);
+  uint32_t k_rem = (PASS == 0) ? k : state->k_rem;
+  uint32_t less = (PASS == 0) ? 0 : state->less_total;
+  uint32_t prefix = (PASS == 0) ? 0 : state->prefix;
+  uint32_t cum = 0;
+  int d = 0;
+  for (; d < nb; ++d) {
+    const uint32_t c = hist[d];
+    if (cum + c >= k_rem) break;
+    cum += c;
+  }
+  if (d == nb) d = nb - 1;  // cannot happen when k <= M
+  state->prefix = prefix | ((uint32_t)d << shift);
+  state->k_rem = k_rem - cum;
+  state->less_total = less + cum;
+  if (PASS == 2) state->need_eq = k_rem - cum;
+}
+
+__global__ void __launch_bounds__(TK_THREADS)
+topk_count_kernel(const float *__restrict__ score, long long M, const TopkState *state,
+                  uint32_t *__restrict__ blk_less, uint32_t *__restrict__ blk_eq) {
+  const uint32_t T = state->prefix;
+  const long long base = (long long)blockIdx.x * TK_TILE;
+  uint32_t nl = 0, ne = 0;
+  for (int t = threadIdx.x; t < TK_TILE; t += TK_THREADS) {
+    const long long i = base + t;
+    if (i < M) {
+      const uint32_t key = score_key(score[i]);
+      nl += key < T;
+      ne += key == T;
+    }
+  }
+  __shared__ uint32_t sl[TK_THREADS / 32], se[TK_THREADS / 32];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    nl += __shfl_xor_sync(FULL, nl, o);
+    ne += __shfl_xor_sync(FULL, ne, o);
+  }
+  if (lane_id() == 0) { sl[threadIdx.x >> 5] = nl; se[threadIdx.x >> 5] = ne; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t a = 0, b = 0;
+    for (int w = 0; w < TK_THREADS / 32; ++w) { a += sl[w]; b += se[w]; }
+    blk_less[blockIdx.x] = a;
+    blk_eq[blockIdx.x] = b;
+  }
+}
+
+// single-block exclusive scan of `a` (and optionally `b`) in place
+__global__ void __launch_bounds__(1024)
+scan_exclusive_kernel(uint32_t *a, uint32_t *b, long long n) {
+  __shared__ uint32_t sa[1024], sb[1024];
+  const int t = threadIdx.x;
+  const long long per = (n + 1023) / 1024;
+  const long long lo = min(n, (long long)t * per), hi = min(n, lo + per);
+  uint32_t xa = 0, xb = 0;
+  for (long long i = lo; i < hi; ++i) { xa += a[i]; if (b) xb += b[i]; }
+  sa[t] = xa; sb[t] = xb;
+  __syncthreads();
+  // Hillis-Steele inclusive scan over 1024 partials
+  for (int o = 1; o < 1024; o <<= 1) {
+    uint32_t ya = 0, yb = 0;
+    if (t >= o) { ya = sa[t - o]; yb = sb[t - o]; }
+    __syncthreads();
+    sa[t] += ya; sb[t] += yb;
+    __syncthreads();
+  }
+  uint32_t ra = sa[t] - xa, rb = sb[t] - xb;  // exclusive base of this thread's chunk
+  for (long long i = lo; i < hi; ++i) {
+    const uint32_t va = a[i]; a[i] = ra; ra += va;
+    if (b) { const uint32_t vb = b[i]; b[i] = rb; rb += vb; }
+  }
+}
+
+__global__ void __launch_bounds__(TK_THREADS)
+topk_write_kernel(const float *__restrict__ score, long long M, const TopkState *state,
+                  const uint32_t *__restrict__ blk_less, const uint32_t *__restrict__ blk_eq,
+                  uint32_t *__restrict__ out_key, uint32_t *__restrict__ out_idx) {
+  const uint32_t T = state->prefix;
+  const uint32_t r = state->need_eq;
+  const long long base = (long long)blockIdx.x * TK_TILE;
+  uint32_t run_less = blk_less[blockIdx.x];  // global #less before the current sub-chunk
+  uint32_t run_eq = blk_eq[blockIdx.x];      // global #eq   before the current sub-chunk
+  __shared__ uint32_t wsum[TK_THREADS / 32];
+  __shared__ uint32_t s_tot;
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  // sub-chunk: 4 consecutive elements per thread, 1024 per block iteration
+  for (int sub = 0; sub < TK_TILE; sub += TK_THREADS * 4) {
+    const long long i0 = base + sub + (long long)threadIdx.x * 4;
+    uint32_t key[4];
+    uint32_t cls[4];  // 1 = less, 0x10000 = eq
+    uint32_t mine = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long long i = i0 + q;
+      key[q] = 0; cls[q] = 0;
+      if (i < M) {
+        key[q] = score_key(score[i]);
+        cls[q] = key[q] < T ? 1u : (key[q] == T ? 0x10000u : 0u);
+      }
+      mine += cls[q];
+    }
+    // packed (less | eq<<16) exclusive block scan; both fields <= 1024
+    uint32_t inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t t = __shfl_up_sync(FULL, inc, d);
+      if (lane >= d) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t acc = 0;
+      for (int w = 0; w < TK_THREADS / 32; ++w) { uint32_t v = wsum[w]; wsum[w] = acc; acc += v; }
+      s_tot = acc;
+    }
+    __syncthreads();
+    uint32_t ex = wsum[warp] + inc - mine;
+    uint32_t lb = run_less + (ex & 0xffffu);
+    uint32_t eb = run_eq + (ex >> 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (cls[q] == 1u) {
+        const uint32_t pos = lb + min(eb, r);
+        out_key[pos] = key[q];
+        out_idx[pos] = (uint32_t)(i0 + q);
+        lb++;
+      } else if (cls[q] == 0x10000u) {
+        if (eb < r) {
+          const uint32_t pos = lb + eb;
+          out_key[pos] = key[q];
+          out_idx[pos] = (uint32_t)(i0 + q);
+        }
+        eb++;
+      }
+    }
+    const uint32_t tot = s_tot;
+    run_less += tot & 0xffffu;
+    run_eq += tot >> 16;
+    __syncthreads();
+  }
+}
+
+// ---------------- stable LSD radix sort of (key, idx) by key, 8 bits per pass ----------------
+
+__global__ void __launch_bounds__(TK_THREADS)
+sort_hist_kernel(const uint32_t *__restrict__ key, uint32_t k, int shift, uint32_t nb,
+                 uint32_t *__restrict__ table /*[256][nb]*/) {
+  __shared__ uint32_t sh[256];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t base = blockIdx.x * SORT_TILE;
+  for (int t = threadIdx.x; t < SORT_TILE; t += TK_THREADS) {
+    const uint32_t i = base + t;
+    if (i < k) atomicAdd(&sh[(key[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  table[(size_t)threadIdx.x * nb + blockIdx.x] = sh[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(TK_THREADS)
+sort_scatter_kernel(const uint32_t *__restrict__ key_in, const uint32_t *__restrict__ idx_in,
+                    uint32_t k, int shift, uint32_t nb, const uint32_t *__restrict__ table,
+                    uint32_t *__restrict__ key_out, uint32_t *__restrict__ idx_out) {
+  __shared__ uint32_t warp_cnt[TK_THREADS / 32][256];
+  __shared__ uint32_t digit_base[256];
+  const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+  digit_base[tid] = table[(size_t)tid * nb + blockIdx.x];
+  const uint32_t base = blockIdx.x * SORT_TILE;
+  for (int sub = 0; sub < SORT_TILE; sub += TK_THREADS) {
+#pragma unroll
+    for (int w = 0; w < TK_THREADS / 32; ++w) warp_cnt[w][tid] = 0;
+    __syncthreads();
+    const uint32_t i = base + sub + tid;
+    const bool valid = i < k;
+    uint32_t kk = 0, ii = 0;
+    if (valid) { kk = key_in[i]; ii = idx_in[i]; }
+    const uint32_t d = valid ? ((kk >> shift) & 255u) : (0x100u | lane);
+    const unsigned peers = __match_any_sync(FULL, d);
+    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    if (valid && rank == 0) warp_cnt[warp][d] = __popc(peers);
+    __syncthreads();
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < TK_THREADS / 32; ++w) {
+      const uint32_t c = warp_cnt[w][tid];
+      warp_cnt[w][tid] = run;
+      run += c;
+    }
+    __syncthreads();
+    if (valid) {
+      const uint32_t pos = digit_base[d] + warp_cnt[warp][d] + rank;
+      key_out[pos] = kk;
+      idx_out[pos] = ii;
+    }
+    __syncthreads();
+    digit_base[tid] += run;
+  }
+}
+
+__global__ void topk_finalize_kernel(const float *__restrict__ score,
+                                     const uint32_t *__restrict__ idx, uint32_t k,
+                                     uint32_t *__restrict__ out_idx, float *__restrict__ out_score) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < k) {
+    const uint32_t p = idx[i];
+    if (out_idx) out_idx[i] = p;
+    if (out_score) out_score[i] = score[p];
+  }
+}
+
+__global__ void pack_edges_kernel(const int *__restrict__ pu, const int *__restrict__ pv,
+                                  const uint32_t *__restrict__ idx, const float *__restrict__ score,
+                                  long long k, float *__restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < k) {
+    const uint32_t p = idx ? idx[i] : (uint32_t)i;
+    out[i * 3 + 0] = (float)pu[p];
+    out[i * 3 + 1] = (float)pv[p];
+    out[i * 3 + 2] = score[i];
+  }
+}
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct TopkLayout {
+  size_t state, hist, blk_less, blk_eq, keyA, keyB, idxA, idxB, table, total;
+  uint32_t nblk, nb_sort;
+};
+
+static TopkLayout topk_layout(int64_t M, int64_t k) {
+  TopkLayout L;
+  L.nblk = (uint32_t)((M + TK_TILE - 1) / TK_TILE);
+  L.nb_sort = (uint32_t)((k + SORT_TILE - 1) / SORT_TILE);
+  size_t o = 0;
+  L.state = o; o += 256;
+  L.hist = o; o += align256(3 * 2048 * sizeof(uint32_t));
+  L.blk_less = o; o += align256((size_t)L.nblk * 4);
+  L.blk_eq = o; o += align256((size_t)L.nblk * 4);
+  L.keyA = o; o += align256((size_t)k * 4);
+  L.keyB = o; o += align256((size_t)k * 4);
+  L.idxA = o; o += align256((size_t)k * 4);
+  L.idxB = o; o += align256((size_t)k * 4);
+  L.table = o; o += align256((size_t)256 * L.nb_sort * 4);
+  L.total = o;
+  return L;
+}
+
+}  // namespace eps
+
+extern "C" size_t eps_topk_workspace_bytes(int64_t M, int64_t k) {
+  if (M <= 0 || k <= 0) return 256;
+  return eps::topk_layout(M, k).total;
+}
+
+extern "C" int eps_topk_f32(const float *score, int64_t M, int64_t k, uint32_t *out_idx,
+                            float *out_score, void *workspace, size_t workspace_bytes,
+                            void *stream_) {
+  using namespace eps;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EPS_CHECK_ARG(score != nullptr, "score is NULL");
+  EPS_CHECK_ARG(out_idx || out_score, "no output requested");
+  EPS_CHECK_ARG(M >= 1 && M < 0xffffffffll, "M out of range [1, 2^32-1)");
+  EPS_CHECK_ARG(k >= 1 && k <= M, "k out of range [1, M]");
+  const int sms = sm_count();
+  if (sms <= 0) { set_error("eps_topk_f32: no CUDA device"); return EPS_ERR_CUDA; }
+  const TopkLayout L = topk_layout(M, k);
+  if (!workspace || workspace_bytes < L.total) {
+    set_error("eps_topk_f32: workspace too small (%zu < %zu)", workspace_bytes, L.total);
+    return EPS_ERR_WORKSPACE;
+  }
+  char *ws = (char *)workspace;
+  TopkState *state = (TopkState *)(ws + L.state);
+  uint32_t *hist = (uint32_t *)(ws + L.hist);
+  uint32_t *blk_less = (uint32_t *)(ws + L.blk_less), *blk_eq = (uint32_t *)(ws + L.blk_eq);
+  uint32_t *keyA = (uint32_t *)(ws + L.keyA), *keyB = (uint32_t *)(ws + L.keyB);
+  uint32_t *idxA = (uint32_t *)(ws + L.idxA), *idxB = (uint32_t *)(ws + L.idxB);
+  uint32_t *table = (uint32_t *)(ws + L.table);
+
+  EPS_CUDA(cudaMemsetAsync(ws + L.state, 0, L.blk_less - L.state, stream));  // state + hist
+  const long long want = (M + TK_THREADS * 8 - 1) / (TK_THREADS * 8);
+  const int hgrid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sms * 8));
+  topk_hist_kernel<0><<<hgrid, TK_THREADS, 0, stream>>>(score, M, state, hist);
+  topk_pick_kernel<0><<<1, 32, 0, stream>>>(state, hist, (uint32_t)k);
+  topk_hist_kernel<1><<<hgrid, TK_THREADS, 0, stream>>>(score, M, state, hist + 2048);
+  topk_pick_kernel<1><<<1, 32, 0, stream>>>(state, hist + 2048, (uint32_t)k);
+  topk_hist_kernel<2><<<hgrid, TK_THREADS, 0, stream>>>(score, M, state, hist + 4096);
+  topk_pick_kernel<2><<<1, 32, 0, stream>>>(state, hist + 4096, (uint32_t)k);
+  EPS_LAUNCH_CHECK();
+  topk_count_kernel<<<L.nblk, TK_THREADS, 0, stream>>>(score, M, state, blk_less, blk_eq);
+  scan_exclusive_kernel<<<1, 1024, 0, stream>>>(blk_less, blk_eq, (long long)L.nblk);
+  topk_write_kernel<<<L.nblk, TK_THREADS, 0, stream>>>(score, M, state, blk_less, blk_eq, keyA, idxA);
+  EPS_LAUNCH_CHECK();
+  uint32_t *kin = keyA, *iin = idxA, *kout = keyB, *iout = idxB;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = pass * 8;
+    sort_hist_kernel<<<L.nb_sort, TK_THREADS, 0, stream>>>(kin, (uint32_t)k, shift, L.nb_sort, table);
+    scan_exclusive_kernel<<<1, 1024, 0, stream>>>(table, nullptr, (long long)256 * L.nb_sort);
+    sort_scatter_kernel<<<L.nb_sort, TK_THREADS, 0, stream>>>(kin, iin, (uint32_t)k, shift, L.nb_sort,
+                                                              table, kout, iout);
+    std::swap(kin, kout);
+    std::swap(iin, iout);
+  }
+  EPS_LAUNCH_CHECK();
+  topk_finalize_kernel<<<(unsigned)((k + 255) / 256), 256, 0, stream>>>(score, iin, (uint32_t)k,
+                                                                       out_idx, out_score);
+  EPS_LAUNCH_CHECK();
+  return EPS_OK;
+}
+
+extern "C" int eps_pack_edges(const int32_t *pair_u, const int32_t *pair_v, const uint32_t *idx,
+                              const float *score, int64_t k, float *out_k3, void *stream_) {
+  using namespace eps;
+  EPS_CHECK_ARG(pair_u && pair_v && score && out_k3, "null pointer");
+  EPS_CHECK_ARG(k >= 0, "negative k");
+  if (k == 0) return EPS_OK;
+  pack_edges_kernel<<<(unsigned)((k + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
+      pair_u, pair_v, idx, score, (long long)k, out_k3);
+  EPS_LAUNCH_CHECK();
+  return EPS_OK;
+}

@@ -1,0 +1,134 @@
+"""The filter step: score every 2-hop non-edge with the filter model, keep the k best.
+
+B200-native restatement of the body of /root/reference/filter.py:92-166:
+
+  reference                                         here
+  ---------                                         ----
+  A2 = adj@adj on one CPU thread, scipy masking     K6 bitmap enumeration per owner slab
+  for batch in DataLoader(range(N), B):             one K2 / K3 launch per slab
+      model(x, edges, adj)   # GNN re-run per batch   embeddings computed once (LinkGNN.embed)
+      cat([edges.t(), score]).cpu()                   scores stay on the device
+  all_scores[:,2].sort(descending=True)  # CPU      K4 radix-select + stable sort of k rows
+  torch.save([N,3])                                 [k,3] float32 (k = N keeps the full list)
+
+Slabs: owners are cut into contiguous ranges holding at most ``slab_pairs`` candidates, each
+slab's top-k is merged into a running top-k by concatenation in slab order + K4 — positions in
+the concatenation preserve the global candidate order, so the result equals a single global
+stable sort.  Multi-GPU: each rank takes a contiguous owner range (parallel.partition_by_work)
+and the per-rank lists are merged with one all-gather (parallel.merge_topk).
+"""
+from __future__ import annotations
+
+from typing import Iterator, Optional, Tuple
+
+import torch
+
+from . import adamic_utils, candidates, ops, parallel
+from .graph import SparseAdj, add_edges
+from .models import GNN_MODELS, LinkGNN
+
+
+def score_edges(model_name: str, model, x, adj: SparseAdj, edges: torch.Tensor,
+                grouped_by_v: bool = True, ra_adj: Optional[SparseAdj] = None) -> torch.Tensor:
+    """Scores of ``edges [2,M]`` under the filter model (/root/reference/filter.py:113-142)."""
+    if model_name in GNN_MODELS:
+        assert isinstance(model, LinkGNN)
+        h = model.embed(x, adj)
+        return model.linkpred.score_pairs(h, edges)
+    if model_name in ("simple", "adamic"):
+        model.grouped_by_v = grouped_by_v
+        return model(x, edges, adj)
+    if model_name == "adamic_ogb":
+        return adamic_utils.AA(adamic_utils.get_A(adj, adj.n), edges, grouped_by_v=grouped_by_v)[0]
+    if model_name == "resource_allocation":
+        A = ra_adj if ra_adj is not None else adj
+        return ops.cn_aa(A, edges, A.ra_weights(), use_values=True, grouped_by_v=grouped_by_v)
+    raise ValueError(f"model {model_name!r} is not a filter model on this path")
+
+
+def ra_graph_from_train_edges(train_edges: torch.Tensor, num_nodes: int) -> SparseAdj:
+    """filter.py:130-139: A rebuilt from the raw train split, both directions, duplicate pairs
+    SUMMED into integer weights (scipy csr_matrix constructor semantics)."""
+    e = train_edges.reshape(-1, 2).long()
+    both = torch.cat([e, e.flip(1)], 0).t()
+    n = int(num_nodes)
+    key = both[0] * n + both[1]
+    ukey, cnt = torch.unique(key, sorted=True, return_counts=True)
+    row = torch.div(ukey, n, rounding_mode="floor")
+    rowptr = torch.zeros(n + 1, dtype=torch.int64, device=e.device)
+    rowptr[1:] = torch.cumsum(torch.bincount(row, minlength=n), 0)
+    val = cnt.float()
+    return SparseAdj(rowptr.int(), (ukey - row * n).int(), None if bool((cnt == 1).all()) else val, n)
+
+
+def iter_slabs(adj: SparseAdj, v_lo: int, v_hi: int, slab_pairs: int) -> Iterator[Tuple[int, int, torch.Tensor]]:
+    """Yield (lo, hi, counts[lo:hi]) owner ranges with at most ``slab_pairs`` candidates each
+    (a single owner with more than that gets a slab of its own)."""
+    if v_hi <= v_lo:
+        return
+    counts = candidates.owner_counts(adj, v_lo, v_hi)
+    cs = torch.cumsum(counts, 0).cpu()
+    lo = 0
+    n_own = v_hi - v_lo
+    base = 0
+    while lo < n_own:
+        hi = int(torch.searchsorted(cs, torch.tensor(base + slab_pairs), right=True).item())
+        hi = max(hi, lo + 1)
+        hi = min(hi, n_own)
+        yield v_lo + lo, v_lo + hi, counts[lo:hi]
+        base = int(cs[hi - 1])
+        lo = hi
+
+
+def _merge_running(running: Optional[torch.Tensor], top: torch.Tensor, k: int) -> torch.Tensor:
+    if running is None:
+        return top
+    cat = torch.cat([running, top], 0)
+    if cat.shape[0] <= k:
+        # both lists are sorted; a stable merge by score == K4 over the concatenation with k = all
+        idx, _ = ops.topk(cat[:, 2].contiguous(), cat.shape[0])
+        return cat[idx]
+    idx, _ = ops.topk(cat[:, 2].contiguous(), k)
+    return cat[idx]
+
+
+@torch.no_grad()
+def filter_topk(model_name: str, model, x, adj: SparseAdj, k: Optional[int] = None,
+                slab_pairs: int = 1 << 27, distributed: bool = False, ra_adj: Optional[SparseAdj] = None,
+                stats: Optional[dict] = None) -> torch.Tensor:
+    """Sorted proposal list, float32 ``[k,3]`` rows (u, v, score) on the device: score descending,
+    ties by the reference's candidate order.  ``k=None`` keeps every candidate like the reference."""
+    rank, world = parallel.world_info() if distributed else (0, 1)
+    v_lo, v_hi = 0, adj.n
+    if world > 1:
+        bounds = parallel.partition_by_work(candidates.two_path_work(adj), world)
+        v_lo, v_hi = bounds[rank], bounds[rank + 1]
+    running = None
+    n_scored = 0
+    for lo, hi, counts in iter_slabs(adj, v_lo, v_hi, slab_pairs):
+        edges = candidates.two_hop(adj, lo, hi, counts)
+        M = edges.shape[1]
+        if M == 0:
+            continue
+        n_scored += M
+        score = score_edges(model_name, model, x, adj, edges, True, ra_adj)
+        kk = M if k is None else min(k, M)
+        top = ops.topk_edges(edges, score, kk)
+        running = top if running is None else _merge_running(running, top, (running.shape[0] + kk) if k is None else k)
+        del edges, score
+    if running is None:
+        running = torch.empty((0, 3), dtype=torch.float32, device=adj.device)
+    if stats is not None:
+        stats["candidates_scored"] = n_scored
+    if world > 1:
+        assert k is not None, "distributed filter needs a proposal size k"
+        running = parallel.merge_topk(running, k)
+    return running
+
+
+def load_extra_edges(path: str, num_sorted_edge: int) -> torch.Tensor:
+    """filter.py:82 / rank.py:294: the first ``num_sorted_edge`` rows of a saved sorted list."""
+    t = torch.load(path)
+    extra = t[:num_sorted_edge, :2].t().long()
+    assert extra.size(0) == 2 and extra.size(1) == num_sorted_edge
+    return extra

@@ -1,0 +1,143 @@
+"""Python-side operators over the C ABI (include/eps.h).  All tensors are CUDA tensors; torch is
+used for allocation and the current stream only.  Nothing here computes on the CPU: a CPU tensor
+or a missing library raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import (EPS_CN_GROUPED_BY_V, EPS_CN_SIGMOID, EPS_MLP_FP32, EPS_MLP_TC_BF16,
+                   EPS_REDUCE_MEAN, EPS_REDUCE_SUM, EpsError, check)
+from .graph import SparseAdj
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise EpsError("edge_proposal_sets_b200 kernels need CUDA tensors (no CPU fallback)")
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _pairs(edges: torch.Tensor):
+    """[2,M] (any int dtype) -> two contiguous int32 rows."""
+    if edges.dim() != 2 or edges.shape[0] != 2:
+        raise EpsError("edges must have shape [2, M]")
+    e = edges if edges.dtype == torch.int32 else edges.to(torch.int32)
+    e = e.contiguous()
+    return e[0], e[1]
+
+
+def spmm_csr(rowptr: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor], x: torch.Tensor,
+             reduce: str = "sum", bias: Optional[torch.Tensor] = None, relu: bool = False,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K1.  y = reduce_j val_ij * x[col_j]  (+bias)(relu)."""
+    _need_cuda(rowptr, col, val, x, bias)
+    lib = _lib.load()
+    x = x.contiguous().float()
+    n_rows = rowptr.numel() - 1
+    F = x.shape[1]
+    y = out if out is not None else torch.empty((n_rows, F), dtype=torch.float32, device=x.device)
+    ws = _ws(lib.eps_spmm_workspace_bytes(), x.device)
+    red = {"sum": EPS_REDUCE_SUM, "add": EPS_REDUCE_SUM, "mean": EPS_REDUCE_MEAN}[reduce]
+    check(lib.eps_spmm_csr_f32(_ptr(rowptr), _ptr(col), _ptr(val), _ptr(x), _ptr(y), n_rows, F, red,
+                               _ptr(None if bias is None else bias.contiguous().float()), int(relu),
+                               _ptr(ws), ws.numel(), _stream()), "eps_spmm_csr_f32")
+    return y
+
+
+def cn_aa(adj: SparseAdj, edges: torch.Tensor, wtable: Optional[torch.Tensor] = None,
+          use_values: bool = True, sigmoid: bool = False, grouped_by_v: bool = False,
+          want_count: bool = False):
+    """K3.  score[i] = sum_{k in N(u)&N(v)} a_u (a_v w_k); optional exact int32 counts."""
+    _need_cuda(adj.col, edges, wtable)
+    lib = _lib.load()
+    pu, pv = _pairs(edges)
+    M = pu.numel()
+    score = torch.empty(M, dtype=torch.float32, device=adj.device)
+    count = torch.empty(M, dtype=torch.int32, device=adj.device) if want_count else None
+    val = adj.val if use_values else None
+    flags = (EPS_CN_SIGMOID if sigmoid else 0) | (EPS_CN_GROUPED_BY_V if grouped_by_v else 0)
+    ws = _ws(lib.eps_cn_aa_workspace_bytes(), adj.device)
+    check(lib.eps_cn_aa(_ptr(adj.rowptr), _ptr(adj.col), _ptr(val), _ptr(wtable), adj.n, _ptr(pu), _ptr(pv),
+                        M, flags, _ptr(score), _ptr(count), _ptr(ws), ws.numel(), _stream()), "eps_cn_aa")
+    return (score, count) if want_count else score
+
+
+def linkpred_mlp(h: torch.Tensor, edges: torch.Tensor, weights: Sequence[torch.Tensor],
+                 biases: Sequence[torch.Tensor], precision: str = "fp32", sigmoid: bool = True) -> torch.Tensor:
+    """K2.  sigmoid(MLP(h[u] * h[v])) for every pair."""
+    _need_cuda(h, edges, *weights, *biases)
+    lib = _lib.load()
+    h = h.contiguous().float()
+    pu, pv = _pairs(edges)
+    M = pu.numel()
+    L = len(weights)
+    Ws = [w.contiguous().float() for w in weights]
+    bs = [b.contiguous().float() for b in biases]
+    n, H = h.shape
+    for l, w in enumerate(Ws):
+        want = (1 if l == L - 1 else H, H)
+        if tuple(w.shape) != want:
+            raise EpsError(f"linkpred layer {l}: weight shape {tuple(w.shape)} != {want}")
+    prec = {"fp32": EPS_MLP_FP32, "bf16": EPS_MLP_TC_BF16, "tc": EPS_MLP_TC_BF16}[precision]
+    Wp = (C.c_void_p * L)(*[w.data_ptr() for w in Ws])
+    bp = (C.c_void_p * L)(*[b.data_ptr() for b in bs])
+    score = torch.empty(M, dtype=torch.float32, device=h.device)
+    ws = _ws(lib.eps_linkpred_workspace_bytes(H, L, prec), h.device)
+    check(lib.eps_linkpred_mlp(_ptr(h), n, H, _ptr(pu), _ptr(pv), M, Wp, bp, L, prec, int(sigmoid),
+                               _ptr(score), _ptr(ws), ws.numel(), _stream()), "eps_linkpred_mlp")
+    return score
+
+
+def topk(score: torch.Tensor, k: int):
+    """K4.  (idx int64 [k], score fp32 [k]) ordered score-descending, ties by position ascending."""
+    _need_cuda(score)
+    lib = _lib.load()
+    score = score.contiguous().float()
+    M = score.numel()
+    k = min(int(k), M)
+    if k <= 0:
+        return (torch.empty(0, dtype=torch.int64, device=score.device),
+                torch.empty(0, dtype=torch.float32, device=score.device))
+    idx = torch.empty(k, dtype=torch.int32, device=score.device)   # uint32 payload
+    out = torch.empty(k, dtype=torch.float32, device=score.device)
+    ws = _ws(lib.eps_topk_workspace_bytes(M, k), score.device)
+    check(lib.eps_topk_f32(_ptr(score), M, k, _ptr(idx), _ptr(out), _ptr(ws), ws.numel(), _stream()),
+          "eps_topk_f32")
+    return idx.long() & 0xFFFFFFFF, out
+
+
+def topk_edges(edges: torch.Tensor, score: torch.Tensor, k: int) -> torch.Tensor:
+    """filter.py:119,160-161 restricted to the first k rows: float32 [k,3] = (u, v, score)."""
+    _need_cuda(edges, score)
+    lib = _lib.load()
+    pu, pv = _pairs(edges)
+    score = score.contiguous().float()
+    M = score.numel()
+    k = min(int(k), M)
+    out = torch.empty((k, 3), dtype=torch.float32, device=score.device)
+    if k == 0:
+        return out
+    idx = torch.empty(k, dtype=torch.int32, device=score.device)
+    sc = torch.empty(k, dtype=torch.float32, device=score.device)
+    ws = _ws(lib.eps_topk_workspace_bytes(M, k), score.device)
+    check(lib.eps_topk_f32(_ptr(score), M, k, _ptr(idx), _ptr(sc), _ptr(ws), ws.numel(), _stream()),
+          "eps_topk_f32")
+    check(lib.eps_pack_edges(_ptr(pu), _ptr(pv), _ptr(idx), _ptr(sc), k, _ptr(out), _stream()),
+          "eps_pack_edges")
+    return out

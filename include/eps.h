@@ -1,0 +1,173 @@
+/*
+ * eps.h — C ABI of libeps_b200.so: the B200 (sm_100a) kernels behind the
+ * Edge-Proposal-Sets filter-and-rank scoring path.
+ *
+ * The reference (CUAI/Edge-Proposal-Sets) is pure Python and has no FFI of its
+ * own; the boundary this library sits behind is the set of Python call sites
+ * below.  Each entry point cites the reference code it
+ * replaces.  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _h;
+ *   - `stream` is a CUstream / cudaStream_t passed as void* (NULL = default
+ *     stream); all work is stream-ordered, no entry point synchronises;
+ *   - the library never allocates device memory: outputs and workspaces are
+ *     caller-owned, sizes come from the *_workspace_bytes functions;
+ *   - node / neighbour indices are int32, CSR columns ascending inside a row,
+ *     no duplicate entries (what rank.add_edges produces after to_symmetric);
+ *   - return value: EPS_OK (0) or a negative eps_status; the message of the
+ *     last failure on the calling thread is eps_last_error();
+ *   - no CPU fallback exists: without a CUDA device every compute entry point
+ *     returns EPS_ERR_CUDA.
+ */
+#ifndef EPS_B200_H
+#define EPS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EPS_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+  EPS_OK = 0,
+  EPS_ERR_INVALID = -1,     /* bad argument (null pointer, negative size, k > M, ...) */
+  EPS_ERR_CUDA = -2,        /* a CUDA runtime call or kernel launch failed */
+  EPS_ERR_WORKSPACE = -3,   /* workspace too small */
+  EPS_ERR_UNSUPPORTED = -4, /* shape outside what the kernel is built for */
+  EPS_ERR_NCCL = -5
+} eps_status;
+
+int eps_version(void);
+const char *eps_last_error(void);
+
+/* ---------------------------------------------------------------------------
+ * K1  CSR SpMM   Y = reduce_j( val_ij * X[col_j,:] ) (+ bias) (ReLU)
+ * replaces: torch_sparse matmul(adj_t, x, reduce='add') inside GCNConv
+ *           (/root/reference/models.py:183,186) and
+ *           matmul(adj_t.set_value(None), x, reduce='mean') inside SAGEConv
+ *           (/root/reference/models.py:436,439).
+ * One warp per row, neighbours folded left-to-right in ascending column order
+ * with fmaf (the accumulation order of torch_sparse's spmm kernel).
+ *   val  == NULL : all ones.        reduce: EPS_REDUCE_SUM | EPS_REDUCE_MEAN
+ *   bias == NULL : none.            relu  : 0 | 1 (applied after bias)
+ * X and Y are row-major [n_cols_of_A, F] / [n_rows, F] fp32 and must not alias.
+ * ------------------------------------------------------------------------- */
+#define EPS_REDUCE_SUM 0
+#define EPS_REDUCE_MEAN 1
+int eps_spmm_csr_f32(const int32_t *rowptr, const int32_t *col, const float *val,
+                     const float *X, float *Y, int32_t n_rows, int32_t F, int reduce,
+                     const float *bias, int relu, void *workspace, size_t workspace_bytes,
+                     void *stream);
+size_t eps_spmm_workspace_bytes(void);
+
+/* ---------------------------------------------------------------------------
+ * K3  Common-Neighbour / Adamic-Adar / Resource-Allocation pair scores
+ * replaces: CommonNeighborsPredictor.forward 'simple' and 'adamic'
+ *           (/root/reference/models.py:536-554), adamic_utils.AA
+ *           (/root/reference/adamic_utils.py:13-25) and
+ *           train_and_eval.resource_allocation
+ *           (/root/reference/train_and_eval.py:195-216).
+ *   score[i] = sum_{k in N(u_i) & N(v_i)} a_u * (a_v * w_k)      (k ascending, fp32)
+ *     a_u = val[u,k], a_v = val[v,k]  (1 when val == NULL)
+ *     w_k = wtable[k]                 (1 when wtable == NULL -> plain CN)
+ *   count[i] = |N(u_i) & N(v_i)|  (int32, exact)
+ *   flags: EPS_CN_SIGMOID        apply 1/(1+exp(-x)) to score (models.py:554)
+ *          EPS_CN_GROUPED_BY_V   promise: equal pair_v values come in long runs
+ *                                (the column-major candidate order of
+ *                                filter.py:96-109); selects the per-owner
+ *                                shared-memory bitmap kernel.  Results are
+ *                                identical with or without the flag.
+ * score or count may be NULL (not both).
+ * ------------------------------------------------------------------------- */
+#define EPS_CN_SIGMOID 1
+#define EPS_CN_GROUPED_BY_V 2
+int eps_cn_aa(const int32_t *rowptr, const int32_t *col, const float *val, const float *wtable,
+              int32_t n, const int32_t *pair_u, const int32_t *pair_v, int64_t M, int flags,
+              float *score, int32_t *count, void *workspace, size_t workspace_bytes,
+              void *stream);
+size_t eps_cn_aa_workspace_bytes(void);
+
+/* ---------------------------------------------------------------------------
+ * K2  LinkPredictor MLP over (u,v) Hadamard pairs
+ * replaces: LinkGNN.forward's h[edges[0]], h[edges[1]] gathers + LinkPredictor.forward
+ *           (/root/reference/models.py:478-485,506).
+ *   z0 = h[u] * h[v];  z_{l+1} = relu(W_l z_l + b_l)  (l < L-1);  out = W_{L-1} z + b
+ *   score = sigmoid(out) (or the logit when apply_sigmoid == 0)
+ * W_h / b_h: HOST arrays of L device pointers; W_l is [out,in] row-major fp32
+ * (nn.Linear layout): [H,H] for l < L-1 and [1,H] for the last layer.
+ * precision: EPS_MLP_FP32    fp32 FFMA on CUDA cores (reference arithmetic)
+ *            EPS_MLP_TC_BF16 bf16 operands, fp32 accumulate, tcgen05.mma + TMEM
+ * ------------------------------------------------------------------------- */
+#define EPS_MLP_FP32 0
+#define EPS_MLP_TC_BF16 1
+int eps_linkpred_mlp(const float *h, int32_t n, int32_t H, const int32_t *pair_u,
+                     const int32_t *pair_v, int64_t M, const float *const *W_h,
+                     const float *const *b_h, int32_t L, int precision, int apply_sigmoid,
+                     float *score, void *workspace, size_t workspace_bytes, void *stream);
+size_t eps_linkpred_workspace_bytes(int32_t H, int32_t L, int precision);
+
+/* ---------------------------------------------------------------------------
+ * K4  top-k proposal selection
+ * replaces: all_scores[:,2].sort(descending=True) + row gather
+ *           (/root/reference/filter.py:160-161) followed by the prefix read
+ *           (/root/reference/rank.py:294).
+ * Radix-select of the k-th score, ordered compaction, stable LSD sort of the
+ * k survivors.  Order contract: score descending, ties by position ascending
+ * (== torch.sort(descending=True, stable=True)); -0.0 == +0.0; NaN first.
+ *   out_idx[j]   = position in `score` of the j-th best element (uint32)
+ *   out_score[j] = score[out_idx[j]]
+ * Requires 1 <= k <= M < 2^32 - 1.
+ * ------------------------------------------------------------------------- */
+int eps_topk_f32(const float *score, int64_t M, int64_t k, uint32_t *out_idx, float *out_score,
+                 void *workspace, size_t workspace_bytes, void *stream);
+size_t eps_topk_workspace_bytes(int64_t M, int64_t k);
+
+/* ---------------------------------------------------------------------------
+ * helpers used by the filter driver (filter.py:113-121 packing)
+ *   eps_pack_edges: out[j] = (float)u[idx[j]], (float)v[idx[j]], score[j]  -> [k,3] fp32
+ * ------------------------------------------------------------------------- */
+int eps_pack_edges(const int32_t *pair_u, const int32_t *pair_v, const uint32_t *idx,
+                   const float *score, int64_t k, float *out_k3, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * K6  2-hop candidate enumeration for the owner range [v_lo, v_hi)
+ * replaces: A2 = adj_t @ adj_t; remove_diag; A2[adj>0] = 0; nonzero
+ *           (/root/reference/filter.py:96-109, CPU, single thread).
+ * Candidates of owner v (= all_edges[:,1]) are every u != v with a common
+ * neighbour and no edge (u,v); they are emitted in ascending u, owners in
+ * ascending v: the reference's column-major order, no sort needed.
+ *   count pass: offsets == NULL -> counts[v - v_lo] = #candidates of v
+ *   fill  pass: offsets[v - v_lo] = exclusive prefix sum of counts (int64);
+ *               pair_u / pair_v receive the (u, v) lists
+ * Needs n/8 + n/256 bytes of shared memory (<= 200 KB, i.e. n <= ~1.6M).
+ * ------------------------------------------------------------------------- */
+int eps_twohop_candidates(const int32_t *rowptr, const int32_t *col, int32_t n, int32_t v_lo,
+                          int32_t v_hi, const int64_t *offsets, uint32_t *counts, int32_t *pair_u,
+                          int32_t *pair_v, void *workspace, size_t workspace_bytes, void *stream);
+size_t eps_twohop_workspace_bytes(void);
+
+/* ---------------------------------------------------------------------------
+ * K5  multi-GPU merge of per-GPU proposal lists (no counterpart in the
+ * single-GPU reference).  One ncclAllGather of the
+ * [k_local,3] fp32 (u, v, score) rows of every rank followed by a K4 select
+ * over the world*k_local gathered rows, executed identically on every rank.
+ * Ranks must own ascending, contiguous owner ranges so that position in the
+ * gathered array preserves the global tie order.  Pad short local lists with
+ * score = -inf rows.  eps_comm_* wrap ncclGetUniqueId / ncclCommInitRank
+ * (resolved by dlopen of libnccl.so.2); id buffers are 128-byte HOST buffers.
+ * ------------------------------------------------------------------------- */
+int eps_comm_unique_id(void *out128_h);
+int eps_comm_init(const void *id128_h, int world, int rank, void **comm_out);
+int eps_comm_destroy(void *comm);
+int eps_topk_merge_allgather(void *comm, const float *local_k3, int64_t k_local, int64_t k,
+                             float *out_k3, void *workspace, size_t workspace_bytes, void *stream);
+size_t eps_topk_merge_workspace_bytes(int world, int64_t k_local, int64_t k);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EPS_B200_H */

@@ -1,0 +1,146 @@
+"""K3 (CN / AA / RA) and K6 (candidate enumeration) on the GPU vs the oracle and the golden
+vectors produced by the reference itself.  Bit-exact for counts and — because the kernels fold
+terms left-to-right in ascending neighbour order like scipy's csr_matvec — for fp32 AA too when
+given the oracle's weight table; <=1e-5 relative with the device-computed table."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import graph as og, heuristics as oh, ranking as orank
+from util import csr_from_undirected, golden_graph, synth_graph, tiny_graphs, to_adj
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return (t.to(dtype) if dtype else t).to(DEV)
+
+
+@pytest.fixture(scope="module", params=["twitch", "fb"])
+def gold(request):
+    z, ei, g = golden_graph(request.param)
+    return request.param, z, g, to_adj(g, DEV)
+
+
+@pytest.mark.parametrize("grouped", [False, True])
+def test_sample_vs_reference_golden(gold, grouped):
+    from edge_proposal_sets_b200 import ops
+    name, z, g, adj = gold
+    e = _dev(z["sample_edges"])
+    score, cnt = ops.cn_aa(adj, e, None, grouped_by_v=grouped, want_count=True)
+    assert np.array_equal(cnt.cpu().numpy(), z["sample_cn"])                       # bit-exact CN
+    assert np.array_equal(score.cpu().numpy(), z["sample_cn"].astype(np.float32))
+    w = _dev(oh.aa_ogb_weights(g))
+    aa = ops.cn_aa(adj, e, w, grouped_by_v=grouped).cpu().numpy()
+    assert np.array_equal(aa, z["sample_aa"])                                      # bit-exact AA (oracle table)
+    aa_dev = ops.cn_aa(adj, e, adj.aa_ogb_weights(), grouped_by_v=grouped).cpu().numpy()
+    ref = z["sample_aa"]
+    assert np.all(np.abs(aa_dev - ref) <= 1e-5 * np.abs(ref) + 1e-12)              # north_star tolerance
+    ra = ops.cn_aa(adj, e, adj.ra_weights(), grouped_by_v=grouped).cpu().numpy()
+    assert np.all(np.abs(ra - z["sample_ra"]) <= 1e-5 * np.abs(z["sample_ra"]) + 1e-12)
+
+
+def test_models_api_simple_adamic(gold):
+    from edge_proposal_sets_b200 import adamic_utils, models
+    name, z, g, adj = gold
+    e = _dev(z["sample_edges"][:, :5000], torch.int64)                              # reference passes int64 [2,B]
+    m = models.CommonNeighborsPredictor(None, 0, None, None, None, None, model_type="simple")
+    assert np.array_equal(m(None, e, adj).cpu().numpy(), z["sample_cn"][:5000].astype(np.float32))
+    m = models.CommonNeighborsPredictor(None, 0, None, None, None, None, model_type="adamic")
+    got = m(None, e, adj).cpu().numpy()
+    want = oh.adamic_sigmoid_pairs(g, z["sample_edges"][:, :5000].astype(np.int64))
+    assert np.max(np.abs(got - want)) <= 1e-6
+    pred, edge = adamic_utils.AA(adamic_utils.get_A(adj, adj.n), e)
+    assert edge is e and np.allclose(pred.cpu().numpy(), z["sample_aa"][:5000], rtol=1e-5, atol=0)
+    ra = adamic_utils.resource_allocation(adj, e.t())
+    assert np.allclose(ra.cpu().numpy(), z["sample_ra"][:5000], rtol=1e-5, atol=0)
+
+
+def test_full_candidate_set_properties(gold):
+    """Full size (twitch: 25,556,294 pairs): K6 reproduces the reference's candidate list byte for
+    byte, the CN checksum, the AA checksum and the exact CN top-k proposal list."""
+    from edge_proposal_sets_b200 import candidates, ops
+    name, z, g, adj = gold
+    edges = candidates.two_hop(adj)
+    N = int(z["num_candidates"])
+    assert edges.shape == (2, N)
+    assert hashlib.sha256(edges.t().contiguous().t().cpu().numpy().tobytes()).hexdigest() == str(z["cand_sha256"])
+    score, cnt = ops.cn_aa(adj, edges, None, grouped_by_v=True, want_count=True)
+    assert int(cnt.long().sum()) == int(z["sum_cn"]) and int(cnt.max()) == int(z["max_cn"])
+    assert int(cnt.min()) >= 1                                                     # every candidate has a 2-path
+    score2 = ops.cn_aa(adj, edges, None, grouped_by_v=False)
+    assert torch.equal(score, score2)                                              # both kernels agree
+    aa = ops.cn_aa(adj, edges, _dev(oh.aa_ogb_weights(g)), grouped_by_v=True)
+    assert abs(float(aa.double().sum()) - float(z["sum_aa"])) <= 1e-9 * float(z["sum_aa"])
+    k = int(z["topk_k"])
+    top = ops.topk_edges(edges, score, k)
+    uv = top[:, :2].to(torch.int32).cpu().numpy()
+    assert hashlib.sha256(np.ascontiguousarray(uv).tobytes()).hexdigest() == str(z["topk_cn_sha256"])
+    assert np.array_equal(uv[:64], z["topk_cn_head"]) and np.array_equal(uv[-64:], z["topk_cn_tail"])
+
+
+def test_weighted_collab_graph():
+    from edge_proposal_sets_b200 import ops
+    s, ei, w, g = synth_graph("small", dataset="collab")
+    wts = np.random.default_rng(3).integers(1, 5, size=ei.shape[1] // 2).astype(np.float32)
+    g = og.add_edges("collab", ei, np.concatenate([wts, wts]), np.zeros((2, 0), np.int64), s["n"])
+    adj = to_adj(g, DEV)
+    assert adj.val is not None
+    cand = og.two_hop_candidates(g)
+    e = _dev(cand)
+    for grouped in (False, True):
+        got = ops.cn_aa(adj, e, None, grouped_by_v=grouped).cpu().numpy()
+        assert np.array_equal(got, oh.cn_scores_pairs(g, cand))                    # sum a_u*a_v, fp32 exact
+        aa = ops.cn_aa(adj, e, _dev(oh.aa_ogb_weights(g)), grouped_by_v=grouped).cpu().numpy()
+        assert np.array_equal(aa, oh.aa_ogb_pairs(g, cand))
+    # random (ungrouped, repeated, self) pairs
+    rng = np.random.default_rng(4)
+    rp = rng.integers(0, s["n"], size=(2, 20000))
+    got, cnt = ops.cn_aa(adj, _dev(rp), None, want_count=True)
+    assert np.array_equal(cnt.cpu().numpy(), oh.cn_count_pairs(g, rp))
+    assert np.array_equal(got.cpu().numpy(), oh.cn_scores_pairs(g, rp))
+
+
+def test_tiny_graphs_and_edge_cases():
+    from edge_proposal_sets_b200 import candidates, ops
+    for name, (n, e) in tiny_graphs().items():
+        g = csr_from_undirected(n, e)
+        adj = to_adj(g, DEV)
+        cand = og.two_hop_candidates(g)
+        got = candidates.two_hop(adj).cpu().numpy()
+        assert np.array_equal(got, cand.astype(np.int32)), name
+        if cand.shape[1] == 0:
+            assert ops.cn_aa(adj, _dev(cand.astype(np.int32))).numel() == 0        # empty input
+            continue
+        for grouped in (False, True):
+            sc, cnt = ops.cn_aa(adj, _dev(cand), _dev(oh.aa_ogb_weights(g)), grouped_by_v=grouped, want_count=True)
+            assert np.array_equal(cnt.cpu().numpy(), oh.cn_count_pairs(g, cand)), name
+            assert np.array_equal(sc.cpu().numpy(), oh.aa_ogb_pairs(g, cand)), name
+    # all pairs incl. isolated nodes and (u,u)
+    n, e = tiny_graphs()["mixed8"]
+    g = csr_from_undirected(n, e)
+    adj = to_adj(g, DEV)
+    allp = np.stack(np.meshgrid(np.arange(n), np.arange(n), indexing="ij")).reshape(2, -1)
+    for grouped in (False, True):
+        cnt = ops.cn_aa(adj, _dev(allp), None, grouped_by_v=grouped, want_count=True)[1].cpu().numpy()
+        assert np.array_equal(cnt, oh.cn_count_pairs(g, allp))
+
+
+@pytest.mark.parametrize("shape", ["tiny", "small"])
+def test_candidate_enumeration_vs_oracle(shape):
+    from edge_proposal_sets_b200 import candidates
+    s, ei, w, g = synth_graph(shape)
+    adj = to_adj(g, DEV)
+    cand = og.two_hop_candidates(g)
+    got = candidates.two_hop(adj)
+    assert np.array_equal(got.cpu().numpy(), cand.astype(np.int32))
+    # owner-range slabs concatenate to the full list
+    mid = s["n"] // 3
+    parts = [candidates.two_hop(adj, 0, mid), candidates.two_hop(adj, mid, s["n"])]
+    assert torch.equal(torch.cat(parts, 1), got)
+    counts = candidates.owner_counts(adj).cpu().numpy()
+    assert np.array_equal(counts, np.bincount(cand[1], minlength=s["n"]))
