@@ -26,6 +26,8 @@ def owner_counts(adj: SparseAdj, v_lo: int = 0, v_hi: int | None = None) -> torc
     ws = _ws(lib.eps_twohop_workspace_bytes(), adj.device)
     check(lib.eps_twohop_candidates(_ptr(adj.rowptr), _ptr(adj.col), adj.n, v_lo, v_hi, None, _ptr(counts),
                                     None, None, _ptr(ws), ws.numel(), _stream()), "eps_twohop_candidates")
+    from . import ops as _ops
+    _ops.LAUNCHES["n"] += 1 if v_hi > v_lo else 0
     return counts.long() & 0xFFFFFFFF
 
 
@@ -48,6 +50,8 @@ def two_hop(adj: SparseAdj, v_lo: int = 0, v_hi: int | None = None, counts: torc
     check(lib.eps_twohop_candidates(_ptr(adj.rowptr), _ptr(adj.col), adj.n, v_lo, v_hi, _ptr(offsets), None,
                                     _ptr(edges[0]), _ptr(edges[1]), _ptr(ws), ws.numel(), _stream()),
           "eps_twohop_candidates")
+    from . import ops as _ops
+    _ops.LAUNCHES["n"] += 1
     return edges
 
 

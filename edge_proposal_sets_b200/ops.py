@@ -15,6 +15,11 @@ from ._lib import (EPS_CN_GROUPED_BY_V, EPS_CN_SIGMOID, EPS_MLP_FP32, EPS_MLP_TC
 from .graph import SparseAdj
 
 
+# kernels launched through this module since the counter was last reset (bench.py reports it)
+LAUNCHES = {"n": 0}
+_TOPK_LAUNCHES = 22      # 3 hist + 3 pick + count + scan + write + 4 x (hist, scan, scatter) + finalize
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -57,6 +62,7 @@ def spmm_csr(rowptr: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor
     check(lib.eps_spmm_csr_f32(_ptr(rowptr), _ptr(col), _ptr(val), _ptr(x), _ptr(y), n_rows, F, red,
                                _ptr(None if bias is None else bias.contiguous().float()), int(relu),
                                _ptr(ws), ws.numel(), _stream()), "eps_spmm_csr_f32")
+    LAUNCHES["n"] += 1
     return y
 
 
@@ -75,6 +81,7 @@ def cn_aa(adj: SparseAdj, edges: torch.Tensor, wtable: Optional[torch.Tensor] = 
     ws = _ws(lib.eps_cn_aa_workspace_bytes(), adj.device)
     check(lib.eps_cn_aa(_ptr(adj.rowptr), _ptr(adj.col), _ptr(val), _ptr(wtable), adj.n, _ptr(pu), _ptr(pv),
                         M, flags, _ptr(score), _ptr(count), _ptr(ws), ws.numel(), _stream()), "eps_cn_aa")
+    LAUNCHES["n"] += 1 if M else 0
     return (score, count) if want_count else score
 
 
@@ -101,6 +108,7 @@ def linkpred_mlp(h: torch.Tensor, edges: torch.Tensor, weights: Sequence[torch.T
     ws = _ws(lib.eps_linkpred_workspace_bytes(H, L, prec), h.device)
     check(lib.eps_linkpred_mlp(_ptr(h), n, H, _ptr(pu), _ptr(pv), M, Wp, bp, L, prec, int(sigmoid),
                                _ptr(score), _ptr(ws), ws.numel(), _stream()), "eps_linkpred_mlp")
+    LAUNCHES["n"] += (2 if prec == EPS_MLP_TC_BF16 else 1) if M else 0
     return score
 
 
@@ -119,6 +127,7 @@ def topk(score: torch.Tensor, k: int):
     ws = _ws(lib.eps_topk_workspace_bytes(M, k), score.device)
     check(lib.eps_topk_f32(_ptr(score), M, k, _ptr(idx), _ptr(out), _ptr(ws), ws.numel(), _stream()),
           "eps_topk_f32")
+    LAUNCHES["n"] += _TOPK_LAUNCHES
     return idx.long() & 0xFFFFFFFF, out
 
 
@@ -140,4 +149,5 @@ def topk_edges(edges: torch.Tensor, score: torch.Tensor, k: int) -> torch.Tensor
           "eps_topk_f32")
     check(lib.eps_pack_edges(_ptr(pu), _ptr(pv), _ptr(idx), _ptr(sc), k, _ptr(out), _stream()),
           "eps_pack_edges")
+    LAUNCHES["n"] += _TOPK_LAUNCHES + 1
     return out

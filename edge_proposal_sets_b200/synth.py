@@ -7,6 +7,8 @@ power-law tail.  Pure numpy; used by bench.py, the tests and the ``*-shape`` dat
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 # name -> n, undirected train edges, power-law exponent, max expected degree, feature width, seed
@@ -66,7 +68,25 @@ def make_shape(name: str, scale: float = 1.0):
     n = max(int(spec["n"] * scale), 16)
     m = max(int(spec["m"] * scale * (scale if spec["gamma"] is None else 1.0)), 16)
     dmax = max(int(min(spec["dmax"], n - 1)), 4)
-    edges = chung_lu(n, m, spec["gamma"], dmax, spec["seed"])
+    # the generator is deterministic, so big shapes are cached on local disk between runs
+    cache = os.path.join(os.environ.get("EPS_SYNTH_CACHE", "/tmp/eps_synth_cache"),
+                         f"{name}_{n}_{m}_{dmax}_{spec['seed']}.npy")
+    edges = None
+    if m >= 1_000_000 and os.path.exists(cache):
+        try:
+            edges = np.load(cache)
+        except Exception:
+            edges = None
+    if edges is None:
+        edges = chung_lu(n, m, spec["gamma"], dmax, spec["seed"])
+        if m >= 1_000_000:
+            try:
+                os.makedirs(os.path.dirname(cache), exist_ok=True)
+                tmp = f"{cache}.{os.getpid()}.tmp.npy"
+                np.save(tmp, edges)
+                os.replace(tmp, cache)
+            except Exception:
+                pass
     rng = np.random.default_rng(spec["seed"] + 1000)
     weight = None
     if spec.get("weighted"):

@@ -1,0 +1,75 @@
+"""K2 tensor-core arm (tcgen05, bf16 operands, fp32 accumulate) vs the fp64 oracle and the fp32 arm.
+
+Stated tolerance: |sigmoid(score) - fp64 oracle| <= 2e-3 absolute and the logit within
+1.5e-2 * (1 + |logit|); the ordering statistics below quantify what that does to a top-k."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gnn as ognn
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _setup(H, L, n, M, seed=0, scale=0.5):
+    sd = ognn.random_state_dict("gcn", n, 0, H, L, seed=seed + 1)
+    rng = np.random.default_rng(seed)
+    h = (rng.standard_normal((n, H)) * scale).astype(np.float32)
+    e = rng.integers(0, n, size=(2, M))
+    Ws = [sd[f"linkpred.lins.{i}.weight"].to(DEV) for i in range(L)]
+    bs = [sd[f"linkpred.lins.{i}.bias"].to(DEV) for i in range(L)]
+    return sd, h, e, Ws, bs
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("H,L,M", [(256, 2, 128), (256, 2, 70001), (256, 3, 40000), (128, 3, 5000), (64, 2, 999)])
+def test_tc_arm_vs_oracle(H, L, M):
+    from edge_proposal_sets_b200 import ops
+    sd, h, e, Ws, bs = _setup(H, L, 5000, M)
+    hd, ed = torch.from_numpy(h).to(DEV), torch.from_numpy(e).to(DEV)
+    got = ops.linkpred_mlp(hd, ed, Ws, bs, "bf16").cpu().numpy()
+    want = ognn.linkpred_forward(torch.from_numpy(h), e, sd, L, torch.float64).numpy()
+    assert np.isfinite(got).all()
+    assert np.max(np.abs(got - want)) <= 2e-3
+    logit = ops.linkpred_mlp(hd, ed, Ws, bs, "bf16", sigmoid=False).cpu().numpy()
+    want_l = ognn.linkpred_forward(torch.from_numpy(h), e, sd, L, torch.float64, return_logit=True).numpy()
+    assert np.max(np.abs(logit - want_l) / (1 + np.abs(want_l))) <= 1.5e-2
+    # determinism: same inputs -> same bits
+    again = ops.linkpred_mlp(hd, ed, Ws, bs, "bf16").cpu().numpy()
+    assert np.array_equal(got, again)
+
+
+@pytest.mark.timeout(120)
+def test_tc_arm_matches_bf16_rounded_oracle_tightly():
+    """With the oracle fed the SAME bf16-rounded operands the only difference left is fp32
+    accumulation order: the kernel must agree to ~1e-5, which pins layouts/descriptors exactly."""
+    from edge_proposal_sets_b200 import ops
+    H, L, M = 256, 3, 20000
+    sd, h, e, Ws, bs = _setup(H, L, 3000, M, seed=3)
+    bf = lambda t: t.to(torch.bfloat16).to(torch.float64)
+    ht = torch.from_numpy(h)
+    z = bf((ht[e[0]] * ht[e[1]]))
+    for i in range(L - 1):
+        z = torch.relu(z @ bf(sd[f"linkpred.lins.{i}.weight"]).t() + sd[f"linkpred.lins.{i}.bias"].double())
+        if i < L - 2:
+            z = bf(z.float())
+    want = (z @ sd[f"linkpred.lins.{L-1}.weight"].double().t()).reshape(-1) + sd[f"linkpred.lins.{L-1}.bias"].double()
+    got = ops.linkpred_mlp(torch.from_numpy(h).to(DEV), torch.from_numpy(e).to(DEV), Ws, bs, "bf16", sigmoid=False)
+    err = np.abs(got.cpu().numpy() - want.numpy())
+    assert err.max() <= 2e-4 * (1 + np.abs(want.numpy()).max())
+
+
+@pytest.mark.timeout(120)
+def test_tc_arm_ranking_quality():
+    from edge_proposal_sets_b200 import ops
+    H, L, M, k = 256, 3, 200000, 20000
+    sd, h, e, Ws, bs = _setup(H, L, 4000, M, seed=5)
+    hd, ed = torch.from_numpy(h).to(DEV), torch.from_numpy(e).to(DEV)
+    tc = ops.linkpred_mlp(hd, ed, Ws, bs, "bf16", sigmoid=False)
+    fp = ops.linkpred_mlp(hd, ed, Ws, bs, "fp32", sigmoid=False)
+    top_tc = set(ops.topk(tc, k)[0].cpu().numpy().tolist())
+    top_fp = set(ops.topk(fp, k)[0].cpu().numpy().tolist())
+    overlap = len(top_tc & top_fp) / k
+    print(f"top-{k} overlap bf16-vs-fp32 arm: {overlap:.4f}")
+    assert overlap >= 0.97
