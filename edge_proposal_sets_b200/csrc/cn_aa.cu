@@ -20,9 +20,20 @@
 
 namespace eps {
 
-constexpr int CN_THREADS = 256;
+constexpr int CN_THREADS = 512;
 constexpr int CN_TILE_PAIRS = 1024;
 constexpr size_t CN_MAX_BITMAP_BYTES = 200 * 1024;
+
+// One warp scores 32 candidates (u_lane, v) against the bitmap of N(v).
+//  phase A  every list with >= CN_LONG neighbours is streamed by the whole warp, aligned to the
+//           list start, four 128-byte loads in flight per lane: one LDG + one shared-memory bit test
+//           + ballot/popc per 32 neighbours;
+//  phase B  the remaining short lists are walked as ONE flattened sequence (lane -> owner list by a
+//           shuffle binary search over the inclusive length prefix), so 32 lists of 3 neighbours cost
+//           3 iterations, not 32.
+// In both phases the weighted terms of a pair are added in ascending-k order (chunks ascending,
+// ballot bits ascending) with __fadd_rn: the score never depends on which phase handled the list.
+constexpr int CN_LONG = 64;
 
 template <bool HAS_W>
 __device__ __forceinline__ void grouped_batch(const int *__restrict__ rowptr,
@@ -39,16 +50,52 @@ __device__ __forceinline__ void grouped_batch(const int *__restrict__ rowptr,
     s = __ldg(rowptr + u);
     len = __ldg(rowptr + u + 1) - s;
   }
-  int pin = len;  // inclusive prefix of the 32 list lengths
+  int c_acc = 0;
+  float a_acc = 0.f;
+  // ---------------- phase A: long lists, one at a time, warp-wide ----------------
+  unsigned longmask = __ballot_sync(FULL, len >= CN_LONG);
+  while (longmask) {
+    const int b = __ffs(longmask) - 1;
+    longmask &= longmask - 1;
+    const int sb = __shfl_sync(FULL, s, b);
+    const int lb = __shfl_sync(FULL, len, b);
+    const int *__restrict__ lp = col + sb;
+    int c = 0;
+    float a = 0.f;
+    for (int off = 0; off < lb; off += 128) {
+      int k[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int p = off + q * 32 + lane;
+        k[q] = p < lb ? __ldg(lp + p) : -1;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const bool hit = k[q] >= 0 && ((bitmap[k[q] >> 5] >> (k[q] & 31)) & 1u);
+        unsigned hm = __ballot_sync(FULL, hit);
+        c += __popc(hm);
+        if (HAS_W && hm) {
+          const float w = hit ? __ldg(wtable + k[q]) : 0.f;
+          while (hm) {  // warp-uniform
+            const int src = __ffs(hm) - 1;
+            hm &= hm - 1;
+            a = __fadd_rn(a, __shfl_sync(FULL, w, src));
+          }
+        }
+      }
+    }
+    if (lane == b) { c_acc = c; a_acc = a; }
+  }
+  // ---------------- phase B: short lists, flattened ----------------
+  const int slen = len >= CN_LONG ? 0 : len;
+  int pin = slen;  // inclusive prefix of the short-list lengths
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     int t = __shfl_up_sync(FULL, pin, d);
     if (lane >= d) pin += t;
   }
-  const int pex = pin - len;
+  const int pex = pin - slen;
   const int total = __shfl_sync(FULL, pin, 31);
-  int c_acc = 0;
-  float a_acc = 0.f;
   for (int j = 0; j < total; j += 32) {
     const int p = j + lane;
     // owner slot of flattened position p = #lists that end at or before p
@@ -239,10 +286,10 @@ extern "C" int eps_cn_aa(const int32_t *rowptr, const int32_t *col, const float 
                          int32_t *count, void *workspace, size_t workspace_bytes, void *stream_) {
   using namespace eps;
   cudaStream_t stream = (cudaStream_t)stream_;
+  EPS_CHECK_ARG(n > 0 && M >= 0, "bad n or M");
+  if (M == 0) return EPS_OK;  // empty pair list: nothing to read or write
   EPS_CHECK_ARG(rowptr && col && pair_u && pair_v, "null graph or pair pointer");
   EPS_CHECK_ARG(score || count, "score and count both NULL");
-  EPS_CHECK_ARG(n > 0 && M >= 0, "bad n or M");
-  if (M == 0) return EPS_OK;
   const int sms = sm_count();
   if (sms <= 0) { set_error("eps_cn_aa: no CUDA device"); return EPS_ERR_CUDA; }
   const size_t bitmap_bytes = (size_t)((n + 31) / 32) * 4;

@@ -48,8 +48,9 @@ extern "C" int eps_linkpred_mlp(const float *h, int32_t n, int32_t H, const int3
                                 size_t workspace_bytes, void *stream_) {
   using namespace eps;
   cudaStream_t stream = (cudaStream_t)stream_;
-  EPS_CHECK_ARG(h && pair_u && pair_v && W_h && b_h && score, "null pointer");
   EPS_CHECK_ARG(n > 0 && M >= 0, "bad n or M");
+  if (M == 0) return EPS_OK;
+  EPS_CHECK_ARG(h && pair_u && pair_v && W_h && b_h && score, "null pointer");
   EPS_CHECK_ARG(L >= 1 && L <= EPS_MAX_MLP_LAYERS, "num_layers out of range [1,8]");
   EPS_CHECK_ARG(H >= 4 && H % 4 == 0 && H <= 512, "hidden size must be a multiple of 4, <= 512");
   EPS_CHECK_ARG(((uintptr_t)h) % 16 == 0, "h must be 16-byte aligned");
