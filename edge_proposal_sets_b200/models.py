@@ -197,7 +197,7 @@ def build_model(args, data, device):
     emb = None
     input_dim = 0
     if args.use_learnable_embedding:
-        emb = nn.Embedding(data.num_nodes, args.hidden_channels).to(device)
+        emb = nn.Embedding(data.num_nodes, args.hidden_channels, device=device)
         input_dim += args.hidden_channels
     if args.use_feature:
         input_dim += data.x.shape[1]
