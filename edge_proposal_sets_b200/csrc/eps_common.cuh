@@ -52,6 +52,8 @@ int linkpred_tc_launch(const float *h, int n, int H, const int *pu, const int *p
                        const MlpParams &prm, int L, int apply_sigmoid, float *score,
                        void *workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t linkpred_tc_workspace_bytes(int H, int L);
+int linkpred_tc3_launch(const float *h, int H, const int *pu, const int *pv, long long M, const MlpParams &prm,
+                        int L, int apply_sigmoid, float *score, uint8_t *img, cudaStream_t stream);
 int linkpred_tc2_launch(const float *h, int H, const int *pu, const int *pv, long long M, const MlpParams &prm,
                         int L, int apply_sigmoid, float *score, uint8_t *img, cudaStream_t stream);
 

@@ -9,6 +9,7 @@
 // and one thread of the leader CTA issues M = 256 MMAs that read both SMs' operands and write each
 // SM's 128 x H fp32 accumulator into its own TMEM.  No weight bytes move after the prologue.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "tc_common.cuh"
 
@@ -210,6 +211,11 @@ int linkpred_tc2_launch(const float *h, int H, const int *pu, const int *pv, lon
   const int total = (L - 1) * H * (H / 8);
   pack_weights_halves_kernel<<<(total + 255) / 256, 256, 0, stream>>>(prm, H, L - 1, img);
   EPS_LAUNCH_CHECK();
+  const char *variant = getenv("EPS_TC_VARIANT");   // "2": force this (unpipelined) kernel
+  if (!(variant && variant[0] == '2')) {
+    const int st = linkpred_tc3_launch(h, H, pu, pv, M, prm, L, apply_sigmoid, score, img, stream);
+    if (st != EPS_ERR_UNSUPPORTED) return st;       // pipelined kernel ran (or failed for real)
+  }
   if (H == 64) return tc2_launch_h<64>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, stream);
   if (H == 128) return tc2_launch_h<128>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, stream);
   return tc2_launch_h<256>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, stream);
