@@ -307,15 +307,22 @@ def run_b200(args):
         num_nodes = n
         x = host["x"]
 
+    copy_stream = torch.cuda.Stream(device=dev)
+
     def upload():
-        """H2D of everything the public call takes: graph, features, weights."""
+        """H2D of everything the public call takes.  The graph goes first on the compute stream
+        (candidate enumeration and CN/AA only need it); features + weights follow on a copy stream
+        and are awaited right before the GCN embeddings are computed."""
         adj = pg.SparseAdj(h_rowptr.to(dev, non_blocking=True), h_col.to(dev, non_blocking=True),
                            None if h_val is None else h_val.to(dev, non_blocking=True), n)
-        x = None if h_x is None else h_x.to(dev, non_blocking=True)
-        with torch.no_grad():                                  # weights: pinned host -> device parameters
+        copy_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(copy_stream), torch.no_grad():
+            x = None if h_x is None else h_x.to(dev, non_blocking=True)
             for k_, p_ in model_skel.state_dict().items():
                 p_.copy_(h_sd[k_], non_blocking=True)
-        return adj, x, model_skel
+            done = torch.cuda.Event()
+            done.record(copy_stream)
+        return adj, x, model_skel, done
 
     model_skel = models.build_model(margs, D, dev)        # parameter storage; every upload() refills it
     model_skel.eval()
@@ -323,7 +330,8 @@ def run_b200(args):
     h2d_bytes = sum(t.numel() * t.element_size() for t in [h_rowptr, h_col] + ([h_val] if h_val is not None else []) +
                     ([h_x] if h_x is not None else []) + list(h_sd.values()))
 
-    adj, x, model = upload()
+    adj, x, model, _ready = upload()
+    torch.cuda.synchronize()
     # ---- choose this rank's owner slab (weak scaling: slab r of ~args.pairs candidates) ----
     counts = candidates.owner_counts(adj).cpu().numpy()
     cum = np.cumsum(counts)
@@ -337,21 +345,23 @@ def run_b200(args):
     slab_pairs = int(cum[hi - 1] - (cum[lo - 1] if lo else 0))
     k = 4_000_000 if slab_pairs >= 16_000_000 else max(slab_pairs // 8, 1)
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    phases = ["candgen", "embed", "cn_aa", "mlp", "topk", "merge"]
+    phases = ["candgen", "cn_aa", "embed", "mlp", "topk", "merge"]
 
-    def step(adj, x, model, record=None):
+    def step(adj, x, model, record=None, weights_ready=None):
         """One filter step on resident inputs.  Returns the two [k,3] proposal lists."""
         marks = [ev() for _ in range(len(phases) + 1)] if record is not None else None
         if marks: marks[0].record()
+        adj._cache.clear()                                    # nothing derived from the graph is reused
         cnt = candidates.owner_counts(adj, lo, hi)
         edges = candidates.two_hop(adj, lo, hi, cnt)
         if marks: marks[1].record()
-        model._h_key = None                                   # no caching across steps:
-        adj._cache.clear()                                    # GCN normalisation is rebuilt too
-        hemb = model.embed(x, adj)
-        if marks: marks[2].record()
         aa_w = adj.aa_ogb_weights()
         aa, cn = ops.cn_aa(adj, edges, aa_w, use_values=adj.val is not None, grouped_by_v=True, want_count=True)
+        if marks: marks[2].record()
+        if weights_ready is not None:
+            torch.cuda.current_stream().wait_event(weights_ready)
+        model._h_key = None                                   # no caching across steps
+        hemb = model.embed(x, adj)                            # gcn_norm + 3 x (GEMM + SpMM)
         if marks: marks[3].record()
         sc = model.linkpred.score_pairs(hemb, edges)
         if marks: marks[4].record()
@@ -366,11 +376,15 @@ def run_b200(args):
             record.append(marks)
         return top_aa, top_nn, edges.shape[1]
 
+    out_host = [torch.empty((k, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
+
     def e2e_step():
-        a, xx, m = upload()
-        ta, tn, M = step(a, xx, m)
-        out = (ta.cpu(), tn.cpu())
-        return out, M
+        a, xx, m, ready = upload()
+        ta, tn, M = step(a, xx, m, weights_ready=ready)
+        out_host[0][: ta.shape[0]].copy_(ta, non_blocking=True)
+        out_host[1][: tn.shape[0]].copy_(tn, non_blocking=True)
+        torch.cuda.current_stream().synchronize()             # the caller holds the result on the host
+        return out_host, M
 
     # ---- algorithmic bytes of the K3 launch (4(d_u+d_v)+12 per pair) ----
     cnt0 = candidates.owner_counts(adj, lo, hi)

@@ -26,6 +26,8 @@ SIGNATURES = {
     "eps_last_error": (C.c_char_p, []),
     "eps_spmm_csr_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _int, _vp, _int, _vp, _sz, _vp]),
     "eps_spmm_workspace_bytes": (_sz, []),
+    "eps_gcn_norm_count": (_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "eps_gcn_norm_fill": (_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "eps_cn_aa": (_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _int, _vp, _vp, _vp, _sz, _vp]),
     "eps_cn_aa_workspace_bytes": (_sz, []),
     "eps_linkpred_mlp": (_int, [_vp, _i32, _i32, _vp, _vp, _i64, C.POINTER(_vp), C.POINTER(_vp), _i32,

@@ -58,13 +58,13 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t mbar_saddr) {
 __device__ __forceinline__ void mbar_arrive_on_cta(uint32_t local_saddr, uint32_t target_cta) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_saddr), "r"(target_cta));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(r) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(r) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t saddr, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred P1;\n\t"
       "LAB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
       "@P1 bra DONE;\n\t"
       "bra LAB_WAIT;\n\t"
       "DONE:\n\t}\n"
@@ -243,71 +243,73 @@ linkpred_tc3_kernel(const float *__restrict__ h, const int *__restrict__ pu, con
     __syncwarp();
   } else {
     // =============================== PRODUCERS ===============================
+    // Lane mapping: 8 consecutive lanes cover one 128-byte row chunk (32 fp32), a warp instruction
+    // reads 4 whole cache lines; rows that share v (the common case inside a run of the
+    // column-major candidate order) coalesce into ONE line request.  Thread handles rows
+    // rg, rg+32, rg+64, rg+96 and the float4 `l8` of each row chunk.
     const int ptid = tid - (P_EPI_WARPS + 1) * 32;          // 0..255
-    const int sub = ptid & 3;                                // 16-byte sub-chunk (8 k values)
-    const int r0 = ptid >> 2, r1 = 64 + (ptid >> 2);         // two rows per thread
+    const int l8 = ptid & 7;
+    const int rg = ptid >> 3;                                // 0..31
     uint32_t stage = 0, eph = 0;
-    long long tile = cluster_id;
-    int u0 = -1, v0 = -1, u1 = -1, v1 = -1;
-    auto load_ids = [&](long long t) {
-      u0 = v0 = u1 = v1 = -1;
-      if (t < npair_tiles) {
-        const long long p0 = t * (2 * TC_BM) + (long long)cta_rank * TC_BM;
-        if (p0 + r0 < M) { u0 = __ldg(pu + p0 + r0); v0 = __ldg(pv + p0 + r0); }
-        if (p0 + r1 < M) { u1 = __ldg(pu + p0 + r1); v1 = __ldg(pv + p0 + r1); }
-      }
-    };
-    float4 cur[8], nxt[8];
-    auto load_chunk = [&](float4 *buf, int c) {
-      const int koff = c * P_CHUNK_K + sub * 8;
-      if (u0 >= 0) {
-        const float4 *a = reinterpret_cast<const float4 *>(h + (size_t)u0 * H + koff);
-        const float4 *b = reinterpret_cast<const float4 *>(h + (size_t)v0 * H + koff);
-        buf[0] = __ldg(a); buf[1] = __ldg(a + 1); buf[2] = __ldg(b); buf[3] = __ldg(b + 1);
-      }
-      if (u1 >= 0) {
-        const float4 *a = reinterpret_cast<const float4 *>(h + (size_t)u1 * H + koff);
-        const float4 *b = reinterpret_cast<const float4 *>(h + (size_t)v1 * H + koff);
-        buf[4] = __ldg(a); buf[5] = __ldg(a + 1); buf[6] = __ldg(b); buf[7] = __ldg(b + 1);
-      }
-    };
-    load_ids(tile);
-    if (tile < npair_tiles) load_chunk(cur, 0);
-    while (tile < npair_tiles) {
-      const bool ok0 = u0 >= 0, ok1 = u1 >= 0;
-      for (int c = 0; c < NCHUNK; ++c) {
-        // prefetch the next chunk (next tile's first chunk at the end of this one)
-        bool nok0 = ok0, nok1 = ok1;
-        if (c + 1 < NCHUNK) {
-          load_chunk(nxt, c + 1);
-        } else {
-          load_ids(tile + nclusters);
-          nok0 = u0 >= 0; nok1 = u1 >= 0;
-          if (tile + nclusters < npair_tiles) load_chunk(nxt, 0);
-        }
-        mbar_wait_cluster(smem_u32(&bars.empty[stage]), eph ^ 1);
-        uint8_t *dst = sRing + stage * P_STAGE_BYTES;
-        uint4 o = make_uint4(0, 0, 0, 0);
-        if (ok0) {
-          o.x = pack_bf16x2(cur[0].x * cur[2].x, cur[0].y * cur[2].y); o.y = pack_bf16x2(cur[0].z * cur[2].z, cur[0].w * cur[2].w);
-          o.z = pack_bf16x2(cur[1].x * cur[3].x, cur[1].y * cur[3].y); o.w = pack_bf16x2(cur[1].z * cur[3].z, cur[1].w * cur[3].w);
-        }
-        *reinterpret_cast<uint4 *>(dst + sw64_chunk_off(r0, sub)) = o;
-        o = make_uint4(0, 0, 0, 0);
-        if (ok1) {
-          o.x = pack_bf16x2(cur[4].x * cur[6].x, cur[4].y * cur[6].y); o.y = pack_bf16x2(cur[4].z * cur[6].z, cur[4].w * cur[6].w);
-          o.z = pack_bf16x2(cur[5].x * cur[7].x, cur[5].y * cur[7].y); o.w = pack_bf16x2(cur[5].z * cur[7].z, cur[5].w * cur[7].w);
-        }
-        *reinterpret_cast<uint4 *>(dst + sw64_chunk_off(r1, sub)) = o;
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.full[stage]), 0);
-        if (++stage == P_RING) { stage = 0; eph ^= 1; }
+    int cu[4], cv[4], nu[4], nv[4];                          // ids: current tile / next tile
+    auto fetch_ids = [&](long long t, int (&uu)[4], int (&vv)[4]) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
-        (void)nok0; (void)nok1;
+      for (int q = 0; q < 4; ++q) {
+        uu[q] = -1; vv[q] = -1;
+        if (t < npair_tiles) {
+          const long long p = t * (2 * TC_BM) + (long long)cta_rank * TC_BM + rg + 32 * q;
+          if (p < M) { uu[q] = __ldg(pu + p); vv[q] = __ldg(pv + p); }
+        }
+      }
+    };
+    float4 bufA[8], bufB[8];
+    auto load_chunk = [&](float4 (&buf)[8], const int (&uu)[4], const int (&vv)[4], int c) {
+      const int koff = c * P_CHUNK_K + l8 * 4;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (uu[q] >= 0) {
+          buf[2 * q] = __ldg(reinterpret_cast<const float4 *>(h + (size_t)uu[q] * H + koff));
+          buf[2 * q + 1] = __ldg(reinterpret_cast<const float4 *>(h + (size_t)vv[q] * H + koff));
+        }
+      }
+    };
+    auto store_chunk = [&](const float4 (&buf)[8], const int (&uu)[4]) {
+      mbar_wait_cluster(smem_u32(&bars.empty[stage]), eph ^ 1);
+      uint8_t *dst = sRing + stage * P_STAGE_BYTES;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = rg + 32 * q;
+        uint2 o = make_uint2(0u, 0u);
+        if (uu[q] >= 0) {
+          const float4 a = buf[2 * q], bb = buf[2 * q + 1];
+          o.x = pack_bf16x2(a.x * bb.x, a.y * bb.y);
+          o.y = pack_bf16x2(a.z * bb.z, a.w * bb.w);
+        }
+        *reinterpret_cast<uint2 *>(dst + sw64_chunk_off(r, l8 >> 1) + (l8 & 1) * 8) = o;
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.full[stage]), 0);
+      if (++stage == P_RING) { stage = 0; eph ^= 1; }
+    };
+    static_assert(NCHUNK % 2 == 0, "two register buffers alternate over an even number of chunks");
+    long long tile = cluster_id;
+    fetch_ids(tile, cu, cv);
+    if (tile < npair_tiles) load_chunk(bufA, cu, cv, 0);
+    while (tile < npair_tiles) {
+      const bool has_next = tile + nclusters < npair_tiles;
+#pragma unroll 1
+      for (int c = 0; c < NCHUNK; c += 2) {
+        load_chunk(bufB, cu, cv, c + 1);                     // in flight while A is converted/stored
+        store_chunk(bufA, cu);
+        if (c == 0) fetch_ids(tile + nclusters, nu, nv);     // ids of the next tile: needed 7 chunks later
+        if (c + 2 < NCHUNK) load_chunk(bufA, cu, cv, c + 2);
+        else if (has_next) load_chunk(bufA, nu, nv, 0);
+        store_chunk(bufB, cu);
       }
       tile += nclusters;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { cu[q] = nu[q]; cv[q] = nv[q]; }
     }
   }
   tc_fence_before();

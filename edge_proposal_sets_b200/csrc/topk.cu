@@ -152,6 +152,77 @@ scan_exclusive_kernel(uint32_t *a, uint32_t *b, long long n) {
   }
 }
 
+// ---- multi-block exclusive scan: local scans of 8192-entry chunks, scan of the chunk totals, fix-up ----
+constexpr int SCAN_CHUNK = 8192;
+
+__global__ void __launch_bounds__(1024)
+scan_local_kernel(uint32_t *a, uint32_t *b, long long n, uint32_t *tot_a, uint32_t *tot_b) {
+  __shared__ uint32_t wa[32], wb[32];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const long long base = (long long)blockIdx.x * SCAN_CHUNK + (long long)t * 8;
+  uint32_t va[8], vb[8];
+  uint32_t sa = 0, sb = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const long long i = base + q;
+    va[q] = i < n ? a[i] : 0u;
+    vb[q] = (b && i < n) ? b[i] : 0u;
+    sa += va[q]; sb += vb[q];
+  }
+  uint32_t ia = sa, ib = sb;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t ya = __shfl_up_sync(FULL, ia, d), yb = __shfl_up_sync(FULL, ib, d);
+    if (lane >= d) { ia += ya; ib += yb; }
+  }
+  if (lane == 31) { wa[warp] = ia; wb[warp] = ib; }
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t xa = wa[lane], xb = wb[lane];
+    uint32_t ja = xa, jb = xb;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t ya = __shfl_up_sync(FULL, ja, d), yb = __shfl_up_sync(FULL, jb, d);
+      if (lane >= d) { ja += ya; jb += yb; }
+    }
+    wa[lane] = ja - xa; wb[lane] = jb - xb;
+    if (lane == 31) { tot_a[blockIdx.x] = ja; if (b) tot_b[blockIdx.x] = jb; }
+  }
+  __syncthreads();
+  uint32_t ra = wa[warp] + ia - sa, rb = wb[warp] + ib - sb;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const long long i = base + q;
+    if (i < n) {
+      a[i] = ra; ra += va[q];
+      if (b) { b[i] = rb; rb += vb[q]; }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+scan_fixup_kernel(uint32_t *a, uint32_t *b, long long n, const uint32_t *tot_a, const uint32_t *tot_b) {
+  const long long base = (long long)blockIdx.x * SCAN_CHUNK;
+  const uint32_t oa = tot_a[blockIdx.x], ob = b ? tot_b[blockIdx.x] : 0u;
+  for (int t = threadIdx.x; t < SCAN_CHUNK; t += 1024) {
+    const long long i = base + t;
+    if (i < n) { a[i] += oa; if (b) b[i] += ob; }
+  }
+}
+
+// exclusive scan of a (and b) in place; tmp holds 2 * ceil(n / SCAN_CHUNK) uint32
+static void scan_exclusive(uint32_t *a, uint32_t *b, long long n, uint32_t *tmp, cudaStream_t stream) {
+  if (n <= SCAN_CHUNK) {
+    scan_exclusive_kernel<<<1, 1024, 0, stream>>>(a, b, n);
+    return;
+  }
+  const int nchunks = (int)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
+  uint32_t *ta = tmp, *tb = tmp + nchunks;
+  scan_local_kernel<<<nchunks, 1024, 0, stream>>>(a, b, n, ta, tb);
+  scan_exclusive_kernel<<<1, 1024, 0, stream>>>(ta, b ? tb : nullptr, (long long)nchunks);
+  scan_fixup_kernel<<<nchunks, 1024, 0, stream>>>(a, b, n, ta, tb);
+}
+
 __global__ void __launch_bounds__(TK_THREADS)
 topk_write_kernel(const float *__restrict__ score, long long M, const TopkState *state,
                   const uint32_t *__restrict__ blk_less, const uint32_t *__restrict__ blk_eq,
@@ -304,7 +375,7 @@ __global__ void pack_edges_kernel(const int *__restrict__ pu, const int *__restr
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct TopkLayout {
-  size_t state, hist, blk_less, blk_eq, keyA, keyB, idxA, idxB, table, total;
+  size_t state, hist, blk_less, blk_eq, keyA, keyB, idxA, idxB, table, scan_tmp, total;
   uint32_t nblk, nb_sort;
 };
 
@@ -322,6 +393,8 @@ static TopkLayout topk_layout(int64_t M, int64_t k) {
   L.idxA = o; o += align256((size_t)k * 4);
   L.idxB = o; o += align256((size_t)k * 4);
   L.table = o; o += align256((size_t)256 * L.nb_sort * 4);
+  const size_t longest = std::max<size_t>(L.nblk, (size_t)256 * L.nb_sort);
+  L.scan_tmp = o; o += align256(2 * ((longest + SCAN_CHUNK - 1) / SCAN_CHUNK + 1) * 4);
   L.total = o;
   return L;
 }
@@ -356,6 +429,7 @@ extern "C" int eps_topk_f32(const float *score, int64_t M, int64_t k, uint32_t *
   uint32_t *keyA = (uint32_t *)(ws + L.keyA), *keyB = (uint32_t *)(ws + L.keyB);
   uint32_t *idxA = (uint32_t *)(ws + L.idxA), *idxB = (uint32_t *)(ws + L.idxB);
   uint32_t *table = (uint32_t *)(ws + L.table);
+  uint32_t *scan_tmp = (uint32_t *)(ws + L.scan_tmp);
 
   EPS_CUDA(cudaMemsetAsync(ws + L.state, 0, L.blk_less - L.state, stream));  // state + hist
   const long long want = (M + TK_THREADS * 8 - 1) / (TK_THREADS * 8);
@@ -368,14 +442,14 @@ extern "C" int eps_topk_f32(const float *score, int64_t M, int64_t k, uint32_t *
   topk_pick_kernel<2><<<1, 32, 0, stream>>>(state, hist + 4096, (uint32_t)k);
   EPS_LAUNCH_CHECK();
   topk_count_kernel<<<L.nblk, TK_THREADS, 0, stream>>>(score, M, state, blk_less, blk_eq);
-  scan_exclusive_kernel<<<1, 1024, 0, stream>>>(blk_less, blk_eq, (long long)L.nblk);
+  scan_exclusive(blk_less, blk_eq, (long long)L.nblk, scan_tmp, stream);
   topk_write_kernel<<<L.nblk, TK_THREADS, 0, stream>>>(score, M, state, blk_less, blk_eq, keyA, idxA);
   EPS_LAUNCH_CHECK();
   uint32_t *kin = keyA, *iin = idxA, *kout = keyB, *iout = idxB;
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = pass * 8;
     sort_hist_kernel<<<L.nb_sort, TK_THREADS, 0, stream>>>(kin, (uint32_t)k, shift, L.nb_sort, table);
-    scan_exclusive_kernel<<<1, 1024, 0, stream>>>(table, nullptr, (long long)256 * L.nb_sort);
+    scan_exclusive(table, nullptr, (long long)256 * L.nb_sort, scan_tmp, stream);
     sort_scatter_kernel<<<L.nb_sort, TK_THREADS, 0, stream>>>(kin, iin, (uint32_t)k, shift, L.nb_sort,
                                                               table, kout, iout);
     std::swap(kin, kout);

@@ -83,6 +83,10 @@ class SparseAdj:
         """(rowptr, col, val) of D^-1/2 (A with diag := 1) D^-1/2, int32/int32/fp32."""
         if "gcn" in self._cache:
             return self._cache["gcn"]
+        if self.col.is_cuda:
+            self._cache["gcn"] = self._gcn_norm_cuda()
+            return self._cache["gcn"]
+        # host tensors (CPU tests of the host logic): the same construction in torch ops
         n, dev = self.n, self.device
         row, col, w = self.row(), self.col.long(), self.values()
         off = row != col
@@ -101,6 +105,27 @@ class SparseAdj:
         out = (rowptr.int(), c.int().contiguous(), val.contiguous())
         self._cache["gcn"] = out
         return out
+
+    def _gcn_norm_cuda(self):
+        """K1b kernels (csrc/gcn_norm.cu): count -> prefix sum -> fill."""
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        n, dev = self.n, self.device
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        dinv = torch.empty(n, dtype=torch.float32, device=dev)
+        newlen = torch.empty(n, dtype=torch.int32, device=dev)
+        _lib.check(lib.eps_gcn_norm_count(p(self.rowptr), p(self.col), p(self.val), n, p(dinv), p(newlen), st),
+                   "eps_gcn_norm_count")
+        rowptr2 = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+        torch.cumsum(newlen, 0, out=rowptr2[1:])
+        nnz2 = self.nnz + n      # upper bound (every row gains at most the diagonal): no host sync
+        col2 = torch.empty(nnz2, dtype=torch.int32, device=dev)
+        val2 = torch.empty(nnz2, dtype=torch.float32, device=dev)
+        _lib.check(lib.eps_gcn_norm_fill(p(self.rowptr), p(self.col), p(self.val), n, p(dinv), p(rowptr2),
+                                         p(col2), p(val2), st), "eps_gcn_norm_fill")
+        return rowptr2, col2, val2
 
     def aa_ogb_weights(self) -> torch.Tensor:
         """1/log(A.sum(0)), inf -> 0 (/root/reference/adamic_utils.py:15-16)."""

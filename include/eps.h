@@ -65,6 +65,22 @@ int eps_spmm_csr_f32(const int32_t *rowptr, const int32_t *col, const float *val
 size_t eps_spmm_workspace_bytes(void);
 
 /* ---------------------------------------------------------------------------
+ * K1b  GCN normalisation  A_hat = D^-1/2 (A with diag := 1) D^-1/2
+ * replaces: torch_geometric gcn_norm inside GCNConv.forward, recomputed on every
+ *           forward by the reference (cached=False, /root/reference/models.py:169-173,183,186).
+ *   count: dinv[i] = (1 + sum_{j != i} w_ij)^-1/2 (inf -> 0); newlen[i] = row length with the
+ *          diagonal entry present
+ *   fill : rowptr2 = exclusive prefix sum of newlen (n+1 entries, caller computes it);
+ *          col2 / val2 = columns with the diagonal merged in sorted position and
+ *          val = (w * dinv[row]) * dinv[col]  (two fp32 roundings, that order)
+ * ------------------------------------------------------------------------- */
+int eps_gcn_norm_count(const int32_t *rowptr, const int32_t *col, const float *val, int32_t n,
+                       float *dinv, int32_t *newlen, void *stream);
+int eps_gcn_norm_fill(const int32_t *rowptr, const int32_t *col, const float *val, int32_t n,
+                      const float *dinv, const int32_t *rowptr2, int32_t *col2, float *val2,
+                      void *stream);
+
+/* ---------------------------------------------------------------------------
  * K3  Common-Neighbour / Adamic-Adar / Resource-Allocation pair scores
  * replaces: CommonNeighborsPredictor.forward 'simple' and 'adamic'
  *           (/root/reference/models.py:536-554), adamic_utils.AA

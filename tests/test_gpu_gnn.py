@@ -137,3 +137,24 @@ def test_filter_topk_end_to_end_cn_and_gcn():
     kth = np.sort(sc64)[::-1][1999]
     assert np.all(sc64[idx] >= kth - 2e-5)                       # nothing outside the tolerance band got in
     assert np.all(np.diff(got[:, 2]) <= 0)
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_gcn_norm_kernels_vs_oracle(weighted):
+    """K1b: diagonal SET to 1 / inserted where missing, dinv = deg^-1/2, (w*dinv_i)*dinv_j."""
+    s, ei, w, g = synth_graph("small", dataset="collab" if weighted else None)
+    if weighted:
+        rng = np.random.default_rng(5)
+        wts = rng.integers(1, 5, size=ei.shape[1] // 2).astype(np.float32)
+        # add a few self loops with odd weights: fill_diag must overwrite them with 1
+        loops = np.stack([np.arange(0, 60, 3), np.arange(0, 60, 3)])
+        ei2 = np.concatenate([ei, loops], 1)
+        w2 = np.concatenate([wts, wts, np.full(loops.shape[1], 7.0, np.float32)])
+        g = og.add_edges("collab", ei2, w2, np.zeros((2, 0), np.int64), s["n"])
+    adj = to_adj(g, DEV)
+    rp, c, v = ognn.gcn_norm(g)
+    rp2, c2, v2 = adj.gcn_norm()
+    assert np.array_equal(rp2.cpu().numpy(), rp)
+    nnz2 = int(rp[-1])
+    assert np.array_equal(c2.cpu().numpy()[:nnz2], c)
+    assert np.allclose(v2.cpu().numpy()[:nnz2], v, rtol=1e-6, atol=0)

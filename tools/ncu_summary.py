@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""Turn ncu outputs pulled back in gpurun_out/ into the small committed summaries under profiles/.
+
+  python tools/ncu_summary.py launches gpurun_out/X_launches.csv profiles/NAME_launches.md
+  python tools/ncu_summary.py raw      gpurun_out/X.ncu-rep      profiles/NAME_kernels.md
+"""
+import collections
+import csv
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
+        "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum"]
+
+
+def launches(src, dst):
+    rows = [r for r in csv.reader(open(src)) if len(r) > 10]
+    hdr = rows[0]
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        try:
+            v = float(r[vi].replace(",", ""))
+        except ValueError:
+            continue
+        a = agg.setdefault(r[ki].split("(")[0][:90], [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(a[1] for a in agg.values())
+    with open(dst, "w") as f:
+        f.write(f"# ncu launch list summary ({src})\n\n`--metrics gpu__time_duration.sum --clock-control none`; "
+                f"cold-cache, serialised: compare SHARES.\nunit: {rows[1][ui]}, total {tot:.0f}\n\n"
+                "| share | total | launches | kernel |\n|---|---|---|---|\n")
+        for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+            f.write(f"| {t / tot * 100:.2f}% | {t:.0f} | {c} | `{k}` |\n")
+
+
+def raw(src, dst):
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    with open(dst, "w") as f:
+        f.write(f"# ncu --set full summary ({src})\n\n")
+        for r in rows[2:]:
+            f.write(f"## `{r[idx['Kernel Name']][:110]}`\n\n| metric | value | unit |\n|---|---|---|\n")
+            for k in KEYS:
+                if k in idx:
+                    f.write(f"| {k} | {r[idx[k]]} | {units[idx[k]]} |\n")
+            f.write("\n")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2], sys.argv[3])
