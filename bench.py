@@ -39,7 +39,8 @@ def parse():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--workload", default="ppa", choices=["ppa", "collab", "ddi", "small", "tiny"])
     p.add_argument("--pairs", type=int, default=1 << 26, help="target candidates per slab per GPU")
-    p.add_argument("--mlp", default=None, choices=[None, "fp32", "bf16"], help="K2 arm (default: best available)")
+    p.add_argument("--mlp", default=None, choices=[None, "fp32", "bf16"],
+                   help="K2 arm: bf16 = tcgen05 tensor-core kernel (default), fp32 = FFMA parity arm")
     p.add_argument("--scale", type=float, default=1.0, help="shrink the synthetic graph (debug only)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -299,7 +300,7 @@ def run_b200(args):
     del adj0
     torch.cuda.empty_cache()
 
-    mlp_arm = args.mlp or os.environ.get("EPS_BENCH_MLP", "fp32")
+    mlp_arm = args.mlp or os.environ.get("EPS_BENCH_MLP", "bf16")
     margs = argparse.Namespace(model="gcn", dataset=args.workload, num_layers=L, hidden_channels=H, dropout=0.0,
                                use_feature=host["x"] is not None, use_learnable_embedding=True, mlp_precision=mlp_arm)
 
