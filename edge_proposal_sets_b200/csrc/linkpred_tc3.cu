@@ -17,6 +17,7 @@
 // The two accumulator slots let the tensor pipe start the next GEMM (next layer, or next tile's first
 // layer) while the epilogue drains the previous one; the ring decouples the HBM/L2 gather from both.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "tc_common.cuh"
 
@@ -25,9 +26,12 @@ namespace eps {
 namespace cg = cooperative_groups;
 
 constexpr int P_EPI_WARPS = 4;
-constexpr int P_PROD_WARPS = 8;
-constexpr int P_THREADS = (P_EPI_WARPS + 1 + P_PROD_WARPS) * 32;   // 416
-constexpr int P_RING = 3;
+constexpr int P_RING = 3;                                          // ring stages == producer groups
+constexpr int P_GROUP_WARPS = 4;                                   // warps per producer group
+constexpr int P_PROD_WARPS = P_RING * P_GROUP_WARPS;               // 12
+constexpr int P_IDS_WARP = P_EPI_WARPS + 1;                        // warp 5 prefetches pair ids
+constexpr int P_FIRST_PROD_WARP = P_EPI_WARPS + 2;
+constexpr int P_THREADS = (P_EPI_WARPS + 2 + P_PROD_WARPS) * 32;   // 576
 constexpr int P_CHUNK_K = 32;
 constexpr int P_STAGE_BYTES = TC_BM * P_CHUNK_K * 2;               // 8 KB
 
@@ -77,13 +81,15 @@ struct PipeBarriers {
   uint64_t acc_full[2];      // MMA commit -> epilogue                     (multicast, both CTAs)
   uint64_t acc_free[2];      // epilogue (both CTAs) -> MMA issuer         (waited in the leader)
   uint64_t a2_full;          // epilogue (both CTAs) -> MMA issuer         (waited in the leader)
+  uint64_t ids_full[2];      // ids warp -> producers                      (CTA-local)
+  uint64_t ids_empty[2];     // producers -> ids warp                      (CTA-local)
 };
 
 template <int H>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
 linkpred_tc3_kernel(const float *__restrict__ h, const int *__restrict__ pu, const int *__restrict__ pv,
                     long long M, const MlpParams prm, int L, int apply_sigmoid,
-                    const uint8_t *__restrict__ wimg, float *__restrict__ score) {
+                    const uint8_t *__restrict__ wimg, float *__restrict__ score, int tune) {
   static_assert(H % 64 == 0 && H >= 64 && H <= 256, "H in {64,128,192,256}");
   constexpr int HH = H / 2;
   constexpr int WH_BYTES = HH * H * 2;
@@ -99,6 +105,7 @@ linkpred_tc3_kernel(const float *__restrict__ h, const int *__restrict__ pu, con
   uint8_t *sA2 = sRing + P_RING * P_STAGE_BYTES;                        // 128 x H bf16 (nhidden >= 2)
   float *sBias = reinterpret_cast<float *>(sA2 + (nhidden >= 2 ? A2_BYTES : 0));
   float *sWlast = sBias + nhidden * H;
+  int2 *sIds = reinterpret_cast<int2 *>(sWlast + H);                    // [2][128] (u, v) of this CTA's rows
   __shared__ __align__(8) PipeBarriers bars;
   __shared__ uint32_t tmem_base_slot;
   cg::cluster_group cluster = cg::this_cluster();
@@ -112,7 +119,7 @@ linkpred_tc3_kernel(const float *__restrict__ h, const int *__restrict__ pu, con
   }
   if (tid == 0) {
     for (int i = 0; i < P_RING; ++i) {
-      mbar_init(smem_u32(&bars.full[i]), 2 * P_PROD_WARPS);
+      mbar_init(smem_u32(&bars.full[i]), 2 * P_GROUP_WARPS);
       mbar_init(smem_u32(&bars.empty[i]), 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -120,6 +127,10 @@ linkpred_tc3_kernel(const float *__restrict__ h, const int *__restrict__ pu, con
       mbar_init(smem_u32(&bars.acc_free[i]), 2 * P_EPI_WARPS);
     }
     mbar_init(smem_u32(&bars.a2_full), 2 * P_EPI_WARPS);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bars.ids_full[i]), 1);
+      mbar_init(smem_u32(&bars.ids_empty[i]), P_PROD_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int l = 0; l < nhidden; ++l) {
@@ -141,15 +152,15 @@ linkpred_tc3_kernel(const float *__restrict__ h, const int *__restrict__ pu, con
 
   if (warp < P_EPI_WARPS) {
     // =============================== EPILOGUE ===============================
-    uint32_t acph[2] = {0, 0};
+    uint32_t acph = 0;            // bit s = phase parity of acc_full[s] (kept in a register)
     uint32_t seq = 0;
     const int row = warp * 32 + lane;
     for (long long tile = cluster_id; tile < npair_tiles; tile += nclusters) {
       const long long p0 = tile * (2 * TC_BM) + (long long)cta_rank * TC_BM;
       for (int l = 0; l < nhidden; ++l, ++seq) {
         const uint32_t slot = seq & 1;
-        mbar_wait_cluster(smem_u32(&bars.acc_full[slot]), acph[slot]);
-        acph[slot] ^= 1;
+        mbar_wait_cluster(smem_u32(&bars.acc_full[slot]), (acph >> slot) & 1u);
+        acph ^= 1u << slot;
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + slot * H;
         const float *bias = sBias + l * H;
@@ -199,13 +210,13 @@ linkpred_tc3_kernel(const float *__restrict__ h, const int *__restrict__ pu, con
     if (cta_rank == 0 && lane == 0) {   // lanes 1..31 wait at the __syncwarp below (keeps the warp
                                         // converged for the aligned cluster barrier at the end)
       uint32_t stage = 0, fph = 0, a2ph = 0, seq = 0;
-      uint32_t afph[2] = {0, 0};
+      uint32_t afph = 0;
       const uint32_t sW_addr = smem_u32(sW), sRing_addr = smem_u32(sRing), sA2_addr = smem_u32(sA2);
       for (long long tile = cluster_id; tile < npair_tiles; tile += nclusters) {
         for (int l = 0; l < nhidden; ++l, ++seq) {
           const uint32_t slot = seq & 1;
-          mbar_wait_cluster(smem_u32(&bars.acc_free[slot]), afph[slot] ^ 1);   // first use of a slot passes
-          afph[slot] ^= 1;
+          mbar_wait_cluster(smem_u32(&bars.acc_free[slot]), ((afph >> slot) & 1u) ^ 1u);   // first use passes
+          afph ^= 1u << slot;
           tc_fence_after();
           const uint32_t d = tmem_base + slot * H;
           if (l == 0) {
@@ -241,75 +252,112 @@ linkpred_tc3_kernel(const float *__restrict__ h, const int *__restrict__ pu, con
       }
     }
     __syncwarp();
+  } else if (warp == P_IDS_WARP) {
+    // =============================== PAIR-ID PREFETCH ===============================
+    // one tile ahead of the producers: (u, v) of this CTA's 128 rows -> shared memory, so the row
+    // gathers never wait on a dependent index load
+    long long tl = 0;
+    for (long long tile = cluster_id; tile < npair_tiles; tile += nclusters, ++tl) {
+      const int slot = (int)(tl & 1);
+      mbar_wait_cluster(smem_u32(&bars.ids_empty[slot]), (uint32_t)(((tl >> 1) & 1) ^ 1));
+      const long long p0 = tile * (2 * TC_BM) + (long long)cta_rank * TC_BM;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = lane + 32 * q;
+        int2 id = make_int2(-1, -1);
+        if (p0 + r < M) { id.x = __ldg(pu + p0 + r); id.y = __ldg(pv + p0 + r); }
+        sIds[slot * TC_BM + r] = id;
+        // pull the whole 1 KB embedding rows of the NEXT tile into L2 now (one DRAM page visit per
+        // row instead of eight chunk-sized ones later); the producers' loads then hit L2
+        const int vprev = __shfl_up_sync(FULL, id.y, 1);
+        if ((tune & 1) && id.x >= 0) {
+          const char *ru = reinterpret_cast<const char *>(h + (size_t)id.x * H);
+#pragma unroll
+          for (int b = 0; b < H * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(ru + b));
+          if (lane == 0 || vprev != id.y) {                  // runs of equal v: prefetch each row once
+            const char *rv = reinterpret_cast<const char *>(h + (size_t)id.y * H);
+#pragma unroll
+            for (int b = 0; b < H * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(rv + b));
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.ids_full[slot]), cta_rank);
+    }
   } else {
     // =============================== PRODUCERS ===============================
-    // Lane mapping: 8 consecutive lanes cover one 128-byte row chunk (32 fp32), a warp instruction
-    // reads 4 whole cache lines; rows that share v (the common case inside a run of the
-    // column-major candidate order) coalesce into ONE line request.  Thread handles rows
-    // rg, rg+32, rg+64, rg+96 and the float4 `l8` of each row chunk.
-    const int ptid = tid - (P_EPI_WARPS + 1) * 32;          // 0..255
-    const int l8 = ptid & 7;
-    const int rg = ptid >> 3;                                // 0..31
-    uint32_t stage = 0, eph = 0;
-    int cu[4], cv[4], nu[4], nv[4];                          // ids: current tile / next tile
-    auto fetch_ids = [&](long long t, int (&uu)[4], int (&vv)[4]) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uu[q] = -1; vv[q] = -1;
-        if (t < npair_tiles) {
-          const long long p = t * (2 * TC_BM) + (long long)cta_rank * TC_BM + rg + 32 * q;
-          if (p < M) { uu[q] = __ldg(pu + p); vv[q] = __ldg(pv + p); }
+    // Three independent groups of four warps; group g owns ring stage g and produces chunks
+    // g, g+3, g+6, ... of the flattened chunk stream of this CTA's tiles.  A warp has ONE batch of
+    // loads in flight at a time (issue 16 x LDG.128, wait for the stage to drain, convert, store,
+    // arrive), so there is no scoreboard coupling between batches; the three groups run out of
+    // phase and keep three chunks (96 KB per SM) in flight.
+    // Lane mapping inside a group (128 threads): 8 consecutive lanes cover one 128-byte row chunk
+    // (32 fp32) so a warp instruction reads 4 whole cache lines, and rows that share v (the
+    // common case inside a run of the column-major candidate order) coalesce into one request.
+    const int pw = warp - P_FIRST_PROD_WARP;                 // 0..11
+    const int group = pw / P_GROUP_WARPS;                    // == ring stage
+    const int t = (pw % P_GROUP_WARPS) * 32 + lane;          // 0..127
+    const int l8 = t & 7;
+    const int rg = t >> 3;                                   // 0..15 ; rows rg + 16 q, q < 8
+    long long my_tiles = 0;
+    if (cluster_id < npair_tiles) my_tiles = (npair_tiles - cluster_id + nclusters - 1) / nclusters;
+    const long long total = my_tiles * NCHUNK;
+    uint8_t *dst = sRing + group * P_STAGE_BYTES;
+    const uint32_t empty_addr = smem_u32(&bars.empty[group]), full_addr = smem_u32(&bars.full[group]);
+    long long cur_tl = -1;
+    int idu[8], idv[8];
+    uint32_t n_use = 0, reuse = 0;
+    for (long long i = group; i < total; i += P_RING, ++n_use) {
+      const long long tl = i / NCHUNK;
+      const int c = (int)(i - tl * NCHUNK);
+      if (tl != cur_tl) {
+        if (cur_tl >= 0) {                                   // done with the previous tile's ids
+          __syncwarp();
+          if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.ids_empty[cur_tl & 1]), cta_rank);
         }
+        mbar_wait_cluster(smem_u32(&bars.ids_full[tl & 1]), (uint32_t)((tl >> 1) & 1));
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int2 id = sIds[(tl & 1) * TC_BM + rg + 16 * q];
+          idu[q] = id.x; idv[q] = id.y;
+        }
+        // rows of one thread that repeat the previous row's v (runs of equal v in the column-major
+        // candidate order) skip the h[v] load and copy the register at consume time
+        reuse = 0;
+        if (tune & 2) {
+#pragma unroll
+          for (int q = 1; q < 8; ++q)
+            if (idu[q] >= 0 && idv[q] == idv[q - 1]) reuse |= 1u << q;
+        }
+        cur_tl = tl;
       }
-    };
-    float4 bufA[8], bufB[8];
-    auto load_chunk = [&](float4 (&buf)[8], const int (&uu)[4], const int (&vv)[4], int c) {
       const int koff = c * P_CHUNK_K + l8 * 4;
+      float4 xu[8], xv[8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (uu[q] >= 0) {
-          buf[2 * q] = __ldg(reinterpret_cast<const float4 *>(h + (size_t)uu[q] * H + koff));
-          buf[2 * q + 1] = __ldg(reinterpret_cast<const float4 *>(h + (size_t)vv[q] * H + koff));
+      for (int q = 0; q < 8; ++q) {
+        if (idu[q] >= 0) {
+          xu[q] = __ldg(reinterpret_cast<const float4 *>(h + (size_t)idu[q] * H + koff));
+          if (!((reuse >> q) & 1u))
+            xv[q] = __ldg(reinterpret_cast<const float4 *>(h + (size_t)idv[q] * H + koff));
         }
       }
-    };
-    auto store_chunk = [&](const float4 (&buf)[8], const int (&uu)[4]) {
-      mbar_wait_cluster(smem_u32(&bars.empty[stage]), eph ^ 1);
-      uint8_t *dst = sRing + stage * P_STAGE_BYTES;
+      mbar_wait_cluster(empty_addr, (n_use & 1) ^ 1);        // the MMAs that read this stage retired
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int r = rg + 32 * q;
+      for (int q = 1; q < 8; ++q)
+        if ((reuse >> q) & 1u) xv[q] = xv[q - 1];            // after the loads have landed: no load-to-load dependency
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int r = rg + 16 * q;
         uint2 o = make_uint2(0u, 0u);
-        if (uu[q] >= 0) {
-          const float4 a = buf[2 * q], bb = buf[2 * q + 1];
-          o.x = pack_bf16x2(a.x * bb.x, a.y * bb.y);
-          o.y = pack_bf16x2(a.z * bb.z, a.w * bb.w);
+        if (idu[q] >= 0) {
+          o.x = pack_bf16x2(xu[q].x * xv[q].x, xu[q].y * xv[q].y);
+          o.y = pack_bf16x2(xu[q].z * xv[q].z, xu[q].w * xv[q].w);
         }
         *reinterpret_cast<uint2 *>(dst + sw64_chunk_off(r, l8 >> 1) + (l8 & 1) * 8) = o;
       }
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.full[stage]), 0);
-      if (++stage == P_RING) { stage = 0; eph ^= 1; }
-    };
-    static_assert(NCHUNK % 2 == 0, "two register buffers alternate over an even number of chunks");
-    long long tile = cluster_id;
-    fetch_ids(tile, cu, cv);
-    if (tile < npair_tiles) load_chunk(bufA, cu, cv, 0);
-    while (tile < npair_tiles) {
-      const bool has_next = tile + nclusters < npair_tiles;
-#pragma unroll 1
-      for (int c = 0; c < NCHUNK; c += 2) {
-        load_chunk(bufB, cu, cv, c + 1);                     // in flight while A is converted/stored
-        store_chunk(bufA, cu);
-        if (c == 0) fetch_ids(tile + nclusters, nu, nv);     // ids of the next tile: needed 7 chunks later
-        if (c + 2 < NCHUNK) load_chunk(bufA, cu, cv, c + 2);
-        else if (has_next) load_chunk(bufA, nu, nv, 0);
-        store_chunk(bufB, cu);
-      }
-      tile += nclusters;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) { cu[q] = nu[q]; cv[q] = nv[q]; }
+      if (lane == 0) mbar_arrive_on_cta(full_addr, 0);
     }
   }
   tc_fence_before();
@@ -324,13 +372,16 @@ static int tc3_launch_h(const float *h, const int *pu, const int *pv, long long 
                         int apply_sigmoid, float *score, uint8_t *img, cudaStream_t stream) {
   const int nhidden = L - 1;
   const size_t smem = 1024 + (size_t)nhidden * (H / 2) * H * 2 + (size_t)P_RING * P_STAGE_BYTES +
-                      (nhidden >= 2 ? (size_t)TC_BM * H * 2 : 0) + sizeof(float) * ((size_t)nhidden * H + H);
+                      (nhidden >= 2 ? (size_t)TC_BM * H * 2 : 0) + sizeof(float) * ((size_t)nhidden * H + H) +
+                      2 * TC_BM * sizeof(int2);
   if (smem > 227 * 1024) return EPS_ERR_UNSUPPORTED;   // caller falls back to linkpred_tc2 / tc
   auto kern = linkpred_tc3_kernel<H>;
   EPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long npair_tiles = (M + 2 * TC_BM - 1) / (2 * TC_BM);
   const int clusters = (int)std::min<long long>(npair_tiles, (long long)(sm_count() / 2));
-  kern<<<2 * clusters, P_THREADS, smem, stream>>>(h, pu, pv, M, prm, L, apply_sigmoid, img, score);
+  const char *tn = getenv("EPS_TC3_TUNE");   // bit0: L2 row prefetch by the id warp, bit1: h[v] register reuse
+  const int tune = tn ? atoi(tn) : 0;
+  kern<<<2 * clusters, P_THREADS, smem, stream>>>(h, pu, pv, M, prm, L, apply_sigmoid, img, score, tune);
   EPS_LAUNCH_CHECK();
   return EPS_OK;
 }

@@ -41,15 +41,22 @@ def _to_undirected(train: np.ndarray, n: int) -> np.ndarray:
 
 def _negatives(n: int, count: int, exist: set, seed: int) -> np.ndarray:
     rng = np.random.default_rng(seed)
-    out = []
-    while len(out) < count:
-        a, b = (int(t) for t in rng.integers(0, n, size=2))
-        p = (min(a, b), max(a, b))
-        if a == b or p in exist:
-            continue
-        exist.add(p)
-        out.append(p)
-    return np.asarray(out, dtype=np.int64).reshape(-1, 2)
+    have = np.fromiter((a * n + b for a, b in exist), dtype=np.int64, count=len(exist))
+    have.sort()
+    out = np.zeros(0, dtype=np.int64)
+    while out.size < count:
+        a = rng.integers(0, n, size=int((count - out.size) * 1.2) + 16)
+        b = rng.integers(0, n, size=a.size)
+        lo, hi = np.minimum(a, b), np.maximum(a, b)
+        key = (lo * n + hi)[lo != hi]
+        pos = np.minimum(np.searchsorted(have, key), max(have.size - 1, 0))
+        key = key[have[pos] != key] if have.size else key
+        _, first = np.unique(key, return_index=True)
+        key = key[np.sort(first)]                              # keep draw order, drop repeats
+        key = key[~np.isin(key, out)]
+        out = np.concatenate([out, key])[:count]
+    exist.update((int(k // n), int(k % n)) for k in out)
+    return np.stack([out // n, out % n], axis=1)
 
 
 class LinkDataset:

@@ -1,0 +1,76 @@
+"""The drop-in CLI (filter.py / rank.py) end to end on the GPU, against the oracle pipeline:
+same argv as submit_job.py emits, same output file name and format."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import graph as og, heuristics as oh, ranking as orank
+from util import golden_graph
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.timeout(280)
+def test_filter_cli_adamic_ogb_then_rank_eval(tmp_path):
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    k = 30000
+    r = subprocess.run([sys.executable, "-u", os.path.join(ROOT, "filter.py"), "--dataset", "fb", "--model", "adamic_ogb",
+                        "--checkpoint", "fb_adamic_ogb||0|0.pt", "--topk", str(k)], cwd=tmp_path, env=env,
+                       capture_output=True, text=True, timeout=250)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = tmp_path / "filtered_edges" / "fb_adamic_ogb__0_0_sorted_edges.pt"     # filter.py:164 naming
+    assert out.exists()
+    got = torch.load(out).numpy()
+    assert got.dtype == np.float32 and got.shape == (k, 3)
+    z, ei, g = golden_graph("fb")
+    cand = og.two_hop_candidates(g)
+    assert f"using {cand.shape[1]} edges" in r.stdout
+    aa_seq = oh.aa_ogb_pairs(g, cand, order="sequential")
+    # device weight table (CUDA logf) vs numpy logf: scores agree to 1e-5 relative, so compare the
+    # list through the oracle's scores of the SAME pairs and require a consistent ordering
+    lookup = {(int(a), int(b)): i for i, (a, b) in enumerate(cand.T)}
+    idx = np.array([lookup[(int(a), int(b))] for a, b in got[:, :2]])
+    assert np.all(np.abs(got[:, 2] - aa_seq[idx]) <= 1e-5 * np.abs(aa_seq[idx]))
+    assert np.all(np.diff(got[:, 2]) <= 0)
+    kth = np.sort(aa_seq)[::-1][k - 1]
+    assert np.all(aa_seq[idx] >= kth * (1 - 2e-5))
+    # rank.py consumes the file: CN rank model ('simple'), two sweep points, Hits@K printed
+    r2 = subprocess.run([sys.executable, "-u", os.path.join(ROOT, "rank.py"), "--dataset", "fb", "--model", "simple",
+                         "--sorted_edge_path", "fb_adamic_ogb__0_0_sorted_edges.pt", "--sweep_min", "0",
+                         "--sweep_max", "20000", "--sweep_num", "2", "--runs", "1"], cwd=tmp_path, env=env,
+                        capture_output=True, text=True, timeout=250)
+    assert r2.returncode == 0, r2.stderr[-2000:]
+    assert "Scheduled extra edges sweep: [0, 10000, 20000] x 1" in r2.stdout
+    assert r2.stdout.count("Hits@20") >= 3
+    assert len(list((tmp_path / "curves").glob("*.pt"))) == 3
+
+
+@pytest.mark.timeout(200)
+def test_rank_side_hits_match_oracle():
+    """evaluate(): Hits@K of the CN rank model on the proposal-augmented graph == oracle (identical)."""
+    from edge_proposal_sets_b200 import models, rank_step
+    from edge_proposal_sets_b200.data import get_data
+    import argparse
+    dev = torch.device("cuda:0")
+    a = argparse.Namespace(dataset="fb", use_feature=False)
+    edge_index, edge_weight, split_edge, data = get_data(a, dev)
+    z, ei, g0 = golden_graph("fb")
+    cand, cn = og.two_hop_candidates(g0, return_values=True)
+    prop = orank.sorted_edges(cand, cn.astype(np.float32), 15000)
+    extra = torch.from_numpy(orank.prefix_edges(prop, 15000))
+    adj, full = rank_step.augmented_graphs("fb", edge_index, edge_weight, extra, split_edge, data.num_nodes, dev)
+    m = models.CommonNeighborsPredictor(None, 0, None, None, None, None, model_type="simple")
+    got = rank_step.evaluate("simple", m, None, adj, full, split_edge, "fb")
+    g = og.add_edges("fb", edge_index.numpy(), edge_weight.numpy(), extra.numpy(), data.num_nodes)
+    sc = lambda e: oh.cn_scores_pairs(g, e.t().numpy())
+    pv, nv = sc(split_edge["valid"]["edge"]), sc(split_edge["valid"]["edge_neg"])
+    pt, nt = sc(split_edge["test"]["edge"]), sc(split_edge["test"]["edge_neg"])
+    ptr = sc(split_edge["eval_train"]["edge"])
+    for K in rank_step.HITS["fb"]:
+        want = (orank.hits_at_k(ptr, nv, K), orank.hits_at_k(pv, nv, K), orank.hits_at_k(pt, nt, K))
+        assert got[f"Hits@{K}"] == pytest.approx(want, abs=0)
