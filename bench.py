@@ -2,8 +2,8 @@
 """bench.py — candidate pairs scored / second on the ogbl-ppa shape (BASELINE.json metric).
 
 One STEP = the whole filter step (/root/reference/filter.py:92-166) for one slab of owner nodes:
-  K6 candidate enumeration (count + fill)  ->  GCN embeddings (3 x [cuBLAS GEMM + K1 SpMM])
-  ->  K3 Adamic-Adar score + exact CN count of every candidate
+  K6 count pass -> K6+K3 fused: candidates + Adamic-Adar score + exact CN count of every candidate
+  ->  GCN embeddings (3 x [cuBLAS GEMM + K1 SpMM])
   ->  K2 GCN+LinkPredictor score of every candidate
   ->  K4 top-k proposal list for each of the two filter models  [-> NCCL all-gather merge, N > 1]
 `value` = candidates of the slab / device time of the step (every candidate is scored by BOTH
@@ -43,6 +43,8 @@ def parse():
                    help="K2 arm: bf16 = tcgen05 tensor-core kernel (default), fp32 = FFMA parity arm")
     p.add_argument("--scale", type=float, default=1.0, help="shrink the synthetic graph (debug only)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--unfused", action="store_true",
+                   help="score CN/AA pair by pair with K3 (eps_cn_aa) after K6 instead of the fused K6+K3 kernel")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
     return p.parse_args()
 
@@ -353,11 +355,15 @@ def run_b200(args):
         marks = [ev() for _ in range(len(phases) + 1)] if record is not None else None
         if marks: marks[0].record()
         adj._cache.clear()                                    # nothing derived from the graph is reused
-        cnt = candidates.owner_counts(adj, lo, hi)
-        edges = candidates.two_hop(adj, lo, hi, cnt)
+        cnt = candidates.owner_counts(adj, lo, hi)             # K6 count pass (sizes the slab)
         if marks: marks[1].record()
         aa_w = adj.aa_ogb_weights()
-        aa, cn = ops.cn_aa(adj, edges, aa_w, use_values=adj.val is not None, grouped_by_v=True, want_count=True)
+        if adj.val is None and not args.unfused:
+            # K6+K3 fused: candidates + AA score + exact CN count from one walk over the 2-paths
+            edges, aa, cn = candidates.two_hop_scored(adj, aa_w, lo, hi, cnt, want_count=True)
+        else:
+            edges = candidates.two_hop(adj, lo, hi, cnt)
+            aa, cn = ops.cn_aa(adj, edges, aa_w, use_values=adj.val is not None, grouped_by_v=True, want_count=True)
         if marks: marks[2].record()
         if weights_ready is not None:
             torch.cuda.current_stream().wait_event(weights_ready)

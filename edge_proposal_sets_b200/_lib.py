@@ -32,12 +32,14 @@ SIGNATURES = {
     "eps_cn_aa_workspace_bytes": (_sz, []),
     "eps_linkpred_mlp": (_int, [_vp, _i32, _i32, _vp, _vp, _i64, C.POINTER(_vp), C.POINTER(_vp), _i32,
                                 _int, _int, _vp, _vp, _sz, _vp]),
-    "eps_linkpred_workspace_bytes": (_sz, [_i32, _i32, _int]),
+    "eps_linkpred_workspace_bytes": (_sz, [_i32, _i32, _i32, _i64, _int]),
     "eps_topk_f32": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     "eps_topk_workspace_bytes": (_sz, [_i64, _i64]),
     "eps_pack_edges": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "eps_twohop_candidates": (_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "eps_twohop_workspace_bytes": (_sz, []),
+    "eps_twohop_scored": (_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "eps_twohop_scored_workspace_bytes": (_sz, [_i64]),
     "eps_comm_unique_id": (_int, [_vp]),
     "eps_comm_init": (_int, [_vp, _int, _int, C.POINTER(_vp)]),
     "eps_comm_destroy": (_int, [_vp]),

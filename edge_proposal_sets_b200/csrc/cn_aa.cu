@@ -3,9 +3,13 @@
 // Replaces /root/reference/models.py:536-554 (index_select + sparse*sparse mul + sparse sum)
 // and /root/reference/adamic_utils.py:20-23 (scipy row-index, csr_elmul_csr, row sum).
 //
-// Two kernels, identical results (per-pair terms are always folded left-to-right in ascending
-// neighbour order with __fadd_rn, the order scipy's csr_matvec / the oracle use, so a score is a
-// function of (graph, u, v) alone — never of batch composition, grid size or GPU count):
+// Two kernels, identical results.  Every per-neighbour term t_k (an fp32 value: w_k, or
+// a_u * (a_v * w_k) on weighted graphs) is converted to 64-bit fixed point with EPS_FX_FRAC_BITS
+// fractional bits and the terms of a pair are added as INTEGERS, so a score is the correctly
+// rounded fp32 value of the exact sum  RN_fp32(sum_k t_k)  — a function of (graph, u, v) alone,
+// never of summation order, batch composition, grid size or GPU count, and bit-identical to the
+// fused enumeration+scoring kernel (twohop_score.cu), which reaches the same sums through atomics.
+// (terms >= 2^-16 are exact in fixed point; smaller ones carry <= 2^-40 absolute error each):
 //
 //  cn_grouped_kernel   the filter hot path.  Candidates arrive in the reference's column-major
 //                      order (filter.py:96-109), i.e. long runs of equal v.  One CTA owns a tile
@@ -31,8 +35,8 @@ constexpr size_t CN_MAX_BITMAP_BYTES = 200 * 1024;
 //  phase B  the remaining short lists are walked as ONE flattened sequence (lane -> owner list by a
 //           shuffle binary search over the inclusive length prefix), so 32 lists of 3 neighbours cost
 //           3 iterations, not 32.
-// In both phases the weighted terms of a pair are added in ascending-k order (chunks ascending,
-// ballot bits ascending) with __fadd_rn: the score never depends on which phase handled the list.
+// In both phases the weighted terms of a pair are added as 64-bit fixed-point integers: the score
+// never depends on which phase handled the list or in which order the terms arrived.
 constexpr int CN_LONG = 64;
 
 template <bool HAS_W>
@@ -51,7 +55,7 @@ __device__ __forceinline__ void grouped_batch(const int *__restrict__ rowptr,
     len = __ldg(rowptr + u + 1) - s;
   }
   int c_acc = 0;
-  float a_acc = 0.f;
+  unsigned long long a_acc = 0ull;
   // ---------------- phase A: long lists, one at a time, warp-wide ----------------
   unsigned longmask = __ballot_sync(FULL, len >= CN_LONG);
   while (longmask) {
@@ -61,7 +65,7 @@ __device__ __forceinline__ void grouped_batch(const int *__restrict__ rowptr,
     const int lb = __shfl_sync(FULL, len, b);
     const int *__restrict__ lp = col + sb;
     int c = 0;
-    float a = 0.f;
+    unsigned long long a = 0ull;      // this lane's share of the list's fixed-point sum
     for (int off = 0; off < lb; off += 128) {
       int k[4];
 #pragma unroll
@@ -74,15 +78,12 @@ __device__ __forceinline__ void grouped_batch(const int *__restrict__ rowptr,
         const bool hit = k[q] >= 0 && ((bitmap[k[q] >> 5] >> (k[q] & 31)) & 1u);
         unsigned hm = __ballot_sync(FULL, hit);
         c += __popc(hm);
-        if (HAS_W && hm) {
-          const float w = hit ? __ldg(wtable + k[q]) : 0.f;
-          while (hm) {  // warp-uniform
-            const int src = __ffs(hm) - 1;
-            hm &= hm - 1;
-            a = __fadd_rn(a, __shfl_sync(FULL, w, src));
-          }
-        }
+        if (HAS_W && hit) a += to_fixed(__ldg(wtable + k[q]));
       }
+    }
+    if (HAS_W) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(FULL, a, o);   // exact: integer adds commute
     }
     if (lane == b) { c_acc = c; a_acc = a; }
   }
@@ -124,12 +125,12 @@ __device__ __forceinline__ void grouped_batch(const int *__restrict__ rowptr,
     unsigned m = hm & segmask;
     c_acc += __popc(m);
     if (HAS_W) {
-      const float w = hit ? __ldg(wtable + k) : 0.f;
+      const unsigned long long w = hit ? to_fixed(__ldg(wtable + k)) : 0ull;
       while (__any_sync(FULL, m != 0)) {
         const int b = m ? (__ffs(m) - 1) : 0;
-        const float t = __shfl_sync(FULL, w, b);
+        const unsigned long long t = __shfl_sync(FULL, w, b);
         if (m) {
-          a_acc = __fadd_rn(a_acc, t);
+          a_acc += t;
           m &= m - 1;
         }
       }
@@ -138,7 +139,7 @@ __device__ __forceinline__ void grouped_batch(const int *__restrict__ rowptr,
   if (valid) {
     if (count) count[base + lane] = c_acc;
     if (score) {
-      float sc = HAS_W ? a_acc : (float)c_acc;
+      float sc = HAS_W ? from_fixed(a_acc) : (float)c_acc;
       if (flags & EPS_CN_SIGMOID) sc = sigmoidf_ref(sc);
       score[base + lane] = sc;
     }
@@ -224,7 +225,7 @@ cn_pairs_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
     const int sa = swp ? sv : su, la = swp ? lv : lu;
     const int sb = swp ? su : sv, lb = swp ? lu : lv;
     int c_acc = 0;
-    float a_acc = 0.f;
+    unsigned long long a_acc = 0ull;
     int hint = 0;
     for (int j = 0; j < la; j += PAIR_G) {
       const int p = j + gl;
@@ -256,19 +257,18 @@ cn_pairs_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
             term = w;
           }
         }
-        unsigned m = hm;
-        while (m) {  // uniform inside the 8-lane group
-          const int b = __ffs(m) - 1;
-          const float t = __shfl_sync(gmask, term, b);
-          a_acc = __fadd_rn(a_acc, t);
-          m &= m - 1;
+        unsigned long long fx = hit ? to_fixed(term) : 0ull;
+        if (hm) {  // uniform inside the 8-lane group; exact integer sum of the group's terms
+#pragma unroll
+          for (int o = PAIR_G / 2; o; o >>= 1) fx += __shfl_xor_sync(gmask, fx, o);
+          a_acc += fx;
         }
       }
     }
     if (gl == 0) {
       if (count) count[pair] = c_acc;
       if (score) {
-        float sc = (HAS_VAL || HAS_W) ? a_acc : (float)c_acc;
+        float sc = (HAS_VAL || HAS_W) ? from_fixed(a_acc) : (float)c_acc;
         if (flags & EPS_CN_SIGMOID) sc = sigmoidf_ref(sc);
         score[pair] = sc;
       }

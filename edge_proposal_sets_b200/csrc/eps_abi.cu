@@ -36,8 +36,8 @@ int sm_count() {
 extern "C" int eps_version(void) { return EPS_VERSION; }
 extern "C" const char *eps_last_error(void) { return eps::g_err; }
 
-extern "C" size_t eps_linkpred_workspace_bytes(int32_t H, int32_t L, int precision) {
-  if (precision == EPS_MLP_TC_BF16) return eps::linkpred_tc_workspace_bytes(H, L);
+extern "C" size_t eps_linkpred_workspace_bytes(int32_t n, int32_t H, int32_t L, int64_t M, int precision) {
+  if (precision == EPS_MLP_TC_BF16) return eps::linkpred_tc_workspace_bytes(n, H, L, M);
   return 256;
 }
 

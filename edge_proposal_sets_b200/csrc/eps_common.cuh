@@ -49,19 +49,36 @@ int linkpred_fp32_launch(const float *h, int H, const int *pu, const int *pv, lo
                          const MlpParams &prm, int L, int apply_sigmoid, float *score,
                          cudaStream_t stream);
 int linkpred_tc_launch(const float *h, int n, int H, const int *pu, const int *pv, long long M,
-                       const MlpParams &prm, int L, int apply_sigmoid, float *score,
-                       void *workspace, size_t workspace_bytes, cudaStream_t stream);
-size_t linkpred_tc_workspace_bytes(int H, int L);
-int linkpred_tc3_launch(const float *h, int H, const int *pu, const int *pv, long long M, const MlpParams &prm,
-                        int L, int apply_sigmoid, float *score, uint8_t *img, cudaStream_t stream);
-int linkpred_tc2_launch(const float *h, int H, const int *pu, const int *pv, long long M, const MlpParams &prm,
-                        int L, int apply_sigmoid, float *score, uint8_t *img, cudaStream_t stream);
+                       const MlpParams &prm, int L, int apply_sigmoid, float *score, void *workspace,
+                       size_t workspace_bytes, cudaStream_t stream);
+size_t linkpred_tc_workspace_bytes(int n, int H, int L, long long M);
+bool linkpred_tc_uses_table(int n, long long M);
+int linkpred_tc3_launch(const void *h, int h_is_bf16, int H, const int *pu, const int *pv, long long M,
+                        const MlpParams &prm, int L, int apply_sigmoid, float *score, uint8_t *img,
+                        cudaStream_t stream);
+int linkpred_tc2_launch(const float *h, const void *h_bf16, int H, const int *pu, const int *pv, long long M,
+                        const MlpParams &prm, int L, int apply_sigmoid, float *score, uint8_t *img,
+                        cudaStream_t stream);
+int h_to_bf16_launch(const float *h, long long elems, void *out, cudaStream_t stream);
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
 __device__ __forceinline__ float sigmoidf_ref(float x) {
   // torch.sigmoid in fp32: 1 / (1 + exp(-x))
   return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+}
+
+// ---- exact pair-score accumulation (K3 and the fused K6+K3 kernel) ----
+// A term t (fp32) becomes the signed 64-bit integer RN(t * 2^EPS_FX_FRAC_BITS); sums of terms are
+// integer sums (order-independent, usable with atomics) and the score is the correctly rounded fp32
+// value of that sum.  Terms with |t| >= 2^-15 are represented exactly (fp32 ulp >= 2^-38), smaller
+// ones carry <= 2^-39 absolute error each; |sum| must stay below 2^25 (n < 2^24 ids, AA terms <= 1.45).
+constexpr int EPS_FX_FRAC_BITS = 38;
+__device__ __forceinline__ unsigned long long to_fixed(float t) {
+  return (unsigned long long)__float2ll_rn(t * 274877906944.0f /* 2^38, exact scaling */);
+}
+__device__ __forceinline__ float from_fixed(unsigned long long s) {
+  return __ll2float_rn((long long)s) * 3.637978807091713e-12f /* 2^-38 */;
 }
 
 // streaming (read-once) loads that do not pollute L1

@@ -97,8 +97,8 @@ linkpred_tc_kernel(const float *__restrict__ h, const int *__restrict__ pu, cons
           const float4 b0 = __ldg(reinterpret_cast<const float4 *>(hv) + 2 * c);
           const float4 b1 = __ldg(reinterpret_cast<const float4 *>(hv) + 2 * c + 1);
           uint4 o;
-          o.x = pack_bf16x2(a0.x * b0.x, a0.y * b0.y); o.y = pack_bf16x2(a0.z * b0.z, a0.w * b0.w);
-          o.z = pack_bf16x2(a1.x * b1.x, a1.y * b1.y); o.w = pack_bf16x2(a1.z * b1.z, a1.w * b1.w);
+          o.x = hadamard_bf16x2(a0.x, a0.y, b0.x, b0.y); o.y = hadamard_bf16x2(a0.z, a0.w, b0.z, b0.w);
+          o.z = hadamard_bf16x2(a1.x, a1.y, b1.x, b1.y); o.w = hadamard_bf16x2(a1.z, a1.w, b1.z, b1.w);
           *reinterpret_cast<uint4 *>(sA + sw128_chunk_off(TC_BM, r, c * 8)) = o;
         }
       } else {
@@ -174,8 +174,17 @@ linkpred_tc_kernel(const float *__restrict__ h, const int *__restrict__ pu, cons
   }
 }
 
-size_t linkpred_tc_workspace_bytes(int H, int L) {
-  return 256 + (size_t)std::max(L - 1, 0) * H * H * 2;
+// The pipelined kernel gathers from a bf16 copy of h (half the bytes per pair) when the pair list
+// is long enough to amortise writing it; short lists read the caller's fp32 rows and round them in
+// registers — the SAME rounding, so the scores do not depend on this choice.
+bool linkpred_tc_uses_table(int n, long long M) { return M >= 2ll * n; }
+
+static size_t tc_img_bytes(int H, int L) {
+  return ((size_t)std::max(L - 1, 0) * H * H * 2 + 255) & ~(size_t)255;
+}
+
+size_t linkpred_tc_workspace_bytes(int n, int H, int L, long long M) {
+  return 256 + tc_img_bytes(H, L) + (linkpred_tc_uses_table(n, M) ? (size_t)n * H * 2 : 0);
 }
 
 template <int H>
@@ -195,13 +204,12 @@ static int tc_launch_h(const float *h, const int *pu, const int *pv, long long M
 int linkpred_tc_launch(const float *h, int n, int H, const int *pu, const int *pv, long long M,
                        const MlpParams &prm, int L, int apply_sigmoid, float *score, void *workspace,
                        size_t workspace_bytes, cudaStream_t stream) {
-  (void)n;
   if (L < 2 || !(H == 64 || H == 128 || H == 256)) {
     set_error("eps_linkpred_mlp: the tcgen05 arm needs num_layers >= 2 and H in {64,128,256} (got L=%d H=%d); "
               "use EPS_MLP_FP32", L, H);
     return EPS_ERR_UNSUPPORTED;
   }
-  if (!workspace || workspace_bytes < linkpred_tc_workspace_bytes(H, L)) {
+  if (!workspace || workspace_bytes < linkpred_tc_workspace_bytes(n, H, L, M)) {
     set_error("eps_linkpred_mlp: workspace too small");
     return EPS_ERR_WORKSPACE;
   }
@@ -209,8 +217,15 @@ int linkpred_tc_launch(const float *h, int n, int H, const int *pu, const int *p
   // CTA-pair kernel (all hidden-layer weights resident) unless EPS_TC_VARIANT=1 asks for the
   // single-CTA kernel (kept for A/B measurements)
   const char *variant = getenv("EPS_TC_VARIANT");
-  if (!(variant && variant[0] == '1') && sm_count() >= 2)
-    return linkpred_tc2_launch(h, H, pu, pv, M, prm, L, apply_sigmoid, score, img, stream);
+  if (!(variant && variant[0] == '1') && sm_count() >= 2) {
+    void *table = nullptr;
+    if (linkpred_tc_uses_table(n, M) && !(variant && variant[0] == '2')) {
+      table = img + tc_img_bytes(H, L);
+      const int st = h_to_bf16_launch(h, (long long)n * H, table, stream);
+      if (st != EPS_OK) return st;
+    }
+    return linkpred_tc2_launch(h, table, H, pu, pv, M, prm, L, apply_sigmoid, score, img, stream);
+  }
   const int total = (L - 1) * H * (H / 8);
   pack_weights_kernel<<<(total + 255) / 256, 256, 0, stream>>>(prm, H, L - 1, img);
   EPS_LAUNCH_CHECK();

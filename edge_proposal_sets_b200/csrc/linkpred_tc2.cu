@@ -116,8 +116,8 @@ linkpred_tc2_kernel(const float *__restrict__ h, const int *__restrict__ pu, con
           const float4 b0 = __ldg(reinterpret_cast<const float4 *>(hv) + 2 * c);
           const float4 b1 = __ldg(reinterpret_cast<const float4 *>(hv) + 2 * c + 1);
           uint4 o;
-          o.x = pack_bf16x2(a0.x * b0.x, a0.y * b0.y); o.y = pack_bf16x2(a0.z * b0.z, a0.w * b0.w);
-          o.z = pack_bf16x2(a1.x * b1.x, a1.y * b1.y); o.w = pack_bf16x2(a1.z * b1.z, a1.w * b1.w);
+          o.x = hadamard_bf16x2(a0.x, a0.y, b0.x, b0.y); o.y = hadamard_bf16x2(a0.z, a0.w, b0.z, b0.w);
+          o.z = hadamard_bf16x2(a1.x, a1.y, b1.x, b1.y); o.w = hadamard_bf16x2(a1.z, a1.w, b1.z, b1.w);
           *reinterpret_cast<uint4 *>(sA + sw128_chunk_off(TC_BM, r, c * 8)) = o;
         }
       } else {
@@ -206,14 +206,16 @@ static int tc2_launch_h(const float *h, const int *pu, const int *pv, long long 
   return EPS_OK;
 }
 
-int linkpred_tc2_launch(const float *h, int H, const int *pu, const int *pv, long long M, const MlpParams &prm,
-                        int L, int apply_sigmoid, float *score, uint8_t *img, cudaStream_t stream) {
+int linkpred_tc2_launch(const float *h, const void *h_bf16, int H, const int *pu, const int *pv, long long M,
+                        const MlpParams &prm, int L, int apply_sigmoid, float *score, uint8_t *img,
+                        cudaStream_t stream) {
   const int total = (L - 1) * H * (H / 8);
   pack_weights_halves_kernel<<<(total + 255) / 256, 256, 0, stream>>>(prm, H, L - 1, img);
   EPS_LAUNCH_CHECK();
   const char *variant = getenv("EPS_TC_VARIANT");   // "2": force this (unpipelined) kernel
   if (!(variant && variant[0] == '2')) {
-    const int st = linkpred_tc3_launch(h, H, pu, pv, M, prm, L, apply_sigmoid, score, img, stream);
+    const int st = h_bf16 ? linkpred_tc3_launch(h_bf16, 1, H, pu, pv, M, prm, L, apply_sigmoid, score, img, stream)
+                          : linkpred_tc3_launch(h, 0, H, pu, pv, M, prm, L, apply_sigmoid, score, img, stream);
     if (st != EPS_ERR_UNSUPPORTED) return st;       // pipelined kernel ran (or failed for real)
   }
   if (H == 64) return tc2_launch_h<64>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, stream);

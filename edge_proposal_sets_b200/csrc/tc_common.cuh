@@ -80,6 +80,19 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t *>(&b);
 }
 
+// A-operand element of the first layer: bf16( bf16(h_u) * bf16(h_v) ).  The embeddings are rounded
+// to bf16 FIRST (the hot path gathers them from a bf16 copy of h: half the bytes per pair), then
+// multiplied; the product of two bf16 values is exact in fp32, so HMUL2.BF16 rounds exactly once.
+// Every tensor-core kernel (tc / tc2 / tc3, fp32 or bf16 source) uses this, so a score does not
+// depend on which kernel or which source format produced it.
+__device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmul2(*reinterpret_cast<const __nv_bfloat162 *>(&a), *reinterpret_cast<const __nv_bfloat162 *>(&b));
+  return *reinterpret_cast<uint32_t *>(&r);
+}
+__device__ __forceinline__ uint32_t hadamard_bf16x2(float a0, float a1, float b0, float b1) {
+  return mul_bf16x2(pack_bf16x2(a0, a1), pack_bf16x2(b0, b1));
+}
+
 // byte offset of the 16-byte chunk holding elements k..k+7 (k % 8 == 0) of row r inside a K-major
 // SWIZZLE_128B tile with `rows` rows: 64-element K blocks, 128-byte rows, chunk index ^= r & 7
 __host__ __device__ __forceinline__ uint32_t sw128_chunk_off(int rows, int r, int k) {

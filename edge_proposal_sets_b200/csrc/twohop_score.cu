@@ -1,0 +1,319 @@
+// K6+K3 fused — 2-hop candidate enumeration WITH Common-Neighbour / Adamic-Adar / RA scores.
+//
+// Replaces /root/reference/filter.py:96-109 followed by the per-batch scoring loop
+// filter.py:113-142 for the heuristic filter models ('simple', 'adamic', 'adamic_ogb',
+// 'resource_allocation').  The reference forms A@A to enumerate candidates, THROWS THE VALUES AWAY
+// (filter.py:108-109) and then re-derives them pair by pair (models.py:536-554,
+// adamic_utils.py:20-23).  But the values are the scores: every 2-path v - k - u contributes one
+// common neighbour k to the pair (u, v), so
+//     CN(u, v) = #2-paths,      AA / RA (u, v) = sum over the 2-paths of w_k .
+// Walking the 2-paths of an owner v costs  sum_{k in N(v)} deg(k)  list elements, whereas scoring
+// its candidates one by one (K3) costs  sum_{u in cand(v)} deg(u)  — ~100x more on the ogbl-ppa
+// shape (mean CN ~ 1.4, mean degree of a candidate ~ 150).
+//
+// One CTA per owner v (handed out dynamically), everything in shared memory but the outputs:
+//   1. mark     bitmap of U = union of N(k), k in N(v)              (flattened coalesced walk)
+//   2. clear    N(v) and v                                           (filter.py:100,103)
+//   3. rank     per-word exclusive popcount prefix (u16 inside a 32-word block + u32 per block),
+//               and emission of pair_u / pair_v in ascending u — the reference's column-major order
+//   4. score    second walk over the same 2-paths: a set bit u -> rank(u) -> one RED.ADD into the
+//               compact accumulator of that candidate (count as int32, weight as 64-bit fixed point,
+//               eps_common.cuh) — integer atomics, hence exact and order-independent
+//   5. cleanup  zero the touched bitmap words
+// A tiny element-wise pass then turns the fixed-point sums into fp32 scores (+ sigmoid).
+// Results are bit-identical to eps_cn_aa on the same pairs.
+#include "eps_common.cuh"
+
+namespace eps {
+
+constexpr int TS_THREADS = 512;
+constexpr int TS_LONG = 96;   // lists at least this long are streamed warp-wide without a search
+
+// Visit every element of the neighbour lists of N(v) (a warp takes 32 lists at a time).
+// f(u, slot) is called once per 2-path v - k - u; `slot` is the lane that holds k's metadata.
+template <typename F>
+__device__ __forceinline__ void walk_two_paths(const int *__restrict__ rowptr, const int *__restrict__ col,
+                                               int vs, int ve, int warp, int nwarps, int lane, F f) {
+  for (int base = vs + warp * 32; base < ve; base += nwarps * 32) {
+    int k = -1, s = 0, len = 0;
+    if (base + lane < ve) {
+      k = __ldg(col + base + lane);
+      s = __ldg(rowptr + k);
+      len = __ldg(rowptr + k + 1) - s;
+    }
+    f.load_slot(k);
+    // ---- long lists: the whole warp streams one list, 4 loads in flight per lane ----
+    unsigned longmask = __ballot_sync(FULL, len >= TS_LONG);
+    while (longmask) {
+      const int b = __ffs(longmask) - 1;
+      longmask &= longmask - 1;
+      const int sb = __shfl_sync(FULL, s, b);
+      const int lb = __shfl_sync(FULL, len, b);
+      f.select_slot(b);
+      const int *__restrict__ lp = col + sb;
+      for (int off = 0; off < lb; off += 128) {
+        int u[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int p = off + q * 32 + lane;
+          u[q] = p < lb ? __ldg(lp + p) : -1;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (u[q] >= 0) f.visit(u[q]);
+      }
+    }
+    // ---- short lists: one flattened sequence ----
+    const int slen = len >= TS_LONG ? 0 : len;
+    int pin = slen;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int t = __shfl_up_sync(FULL, pin, d);
+      if (lane >= d) pin += t;
+    }
+    const int pex = pin - slen;
+    const int total = __shfl_sync(FULL, pin, 31);
+    for (int j = 0; j < total; j += 32) {
+      const int p = j + lane;
+      int lo = 0;
+#pragma unroll
+      for (int step = 16; step >= 1; step >>= 1) {
+        int t = __shfl_sync(FULL, pin, lo + step - 1);
+        if (t <= p) lo += step;
+      }
+      const int s_t = __shfl_sync(FULL, s, lo);
+      const int pe_t = __shfl_sync(FULL, pex, lo);
+      f.select_slot_lane(lo);
+      if (p < total) f.visit(__ldg(col + s_t + (p - pe_t)));
+    }
+  }
+}
+
+struct MarkVisitor {
+  uint32_t *bm, *bm2;
+  __device__ __forceinline__ void load_slot(int) {}
+  __device__ __forceinline__ void select_slot(int) {}
+  __device__ __forceinline__ void select_slot_lane(int) {}
+  __device__ __forceinline__ void visit(int u) {
+    const uint32_t bit = 1u << (u & 31);
+    const int w = u >> 5;
+    if (!(bm[w] & bit)) {                          // cheap pre-test: most bits are already set
+      const uint32_t old = atomicOr(&bm[w], bit);
+      if (old == 0) atomicOr(&bm2[w >> 5], 1u << (w & 31));
+    }
+  }
+};
+
+template <bool HAS_W, bool WANT_CN>
+struct ScoreVisitor {
+  const uint32_t *bm, *blk;
+  const uint16_t *pre;
+  const float *__restrict__ wtable;
+  unsigned long long *acc;   // + out_base already applied
+  int *cn;
+  unsigned long long fx_slot = 0ull, fx = 0ull;
+  __device__ __forceinline__ void load_slot(int k) {
+    if (HAS_W) fx_slot = k >= 0 ? to_fixed(__ldg(wtable + k)) : 0ull;
+  }
+  __device__ __forceinline__ void select_slot(int b) {           // warp-uniform slot
+    if (HAS_W) fx = __shfl_sync(FULL, fx_slot, b);
+  }
+  __device__ __forceinline__ void select_slot_lane(int lo) {     // per-lane slot
+    if (HAS_W) fx = __shfl_sync(FULL, fx_slot, lo);
+  }
+  __device__ __forceinline__ void visit(int u) {
+    const int w = u >> 5, b = u & 31;
+    const uint32_t word = bm[w];
+    if ((word >> b) & 1u) {
+      const uint32_t idx = blk[w >> 5] + pre[w] + __popc(word & ((1u << b) - 1u));
+      if (HAS_W) atomicAdd(acc + idx, fx);
+      if (WANT_CN) atomicAdd(cn + idx, 1);
+    }
+  }
+};
+
+template <bool HAS_W, bool WANT_CN>
+__global__ void __launch_bounds__(TS_THREADS)
+twohop_score_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
+                    const float *__restrict__ wtable, int n, int v_lo, int v_hi,
+                    const long long *__restrict__ offsets, int *__restrict__ pair_u,
+                    int *__restrict__ pair_v, unsigned long long *__restrict__ acc, int *__restrict__ cn,
+                    unsigned int *owner_counter) {
+  extern __shared__ uint32_t sm[];
+  const int W = (n + 31) >> 5;       // bitmap words
+  const int W2 = (W + 31) >> 5;      // blocks of 32 words
+  uint32_t *bm = sm;
+  uint32_t *bm2 = bm + W;            // one bit per non-zero bitmap word
+  uint32_t *blk = bm2 + W2;          // #candidates before block g
+  uint16_t *pre = reinterpret_cast<uint16_t *>(blk + W2);   // #candidates before word w inside its block
+  __shared__ int s_owner;
+  __shared__ uint32_t s_scan[TS_THREADS / 32];
+  __shared__ uint32_t s_carry;
+  const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+  constexpr int NW = TS_THREADS / 32;
+  for (int w = tid; w < W + W2; w += TS_THREADS) sm[w] = 0;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_owner = v_lo + (int)atomicAdd(owner_counter, 1u);
+    __syncthreads();
+    const int v = s_owner;
+    if (v >= v_hi) break;
+    const int vs = __ldg(rowptr + v), ve = __ldg(rowptr + v + 1);
+    const long long out_base = offsets[v - v_lo];
+    if (offsets[v - v_lo + 1] == out_base) continue;   // no candidates (uniform): bitmap untouched
+    // ---- 1. mark ----
+    walk_two_paths(rowptr, col, vs, ve, warp, NW, lane, MarkVisitor{bm, bm2});
+    __syncthreads();
+    // ---- 2. clear known edges and the diagonal ----
+    for (int p = vs + tid; p < ve; p += TS_THREADS) {
+      const int k = __ldg(col + p);
+      atomicAnd(&bm[k >> 5], ~(1u << (k & 31)));
+    }
+    if (tid == 0) atomicAnd(&bm[v >> 5], ~(1u << (v & 31)));
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    // ---- 3. rank + emit; thread t owns block c + t (32 bitmap words) ----
+    for (int c = 0; c < W2; c += TS_THREADS) {
+      const int g = c + tid;
+      const uint32_t m2 = (g < W2) ? bm2[g] : 0u;
+      uint32_t cnt = 0;
+      {
+        uint32_t m = m2;
+        while (m) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          cnt += __popc(bm[g * 32 + b]);
+        }
+      }
+      uint32_t inc = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(FULL, inc, d);
+        if (lane >= d) inc += t;
+      }
+      if (lane == 31) s_scan[warp] = inc;
+      __syncthreads();
+      uint32_t wbase = 0, tot = 0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        const uint32_t x = s_scan[w];
+        if (w < warp) wbase += x;
+        tot += x;
+      }
+      const uint32_t carry = s_carry;
+      const uint32_t first = carry + wbase + (inc - cnt);
+      if (g < W2) blk[g] = first;
+      long long o = out_base + first;
+      uint32_t r = 0;
+      uint32_t m = m2;
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        const int w = g * 32 + b;
+        uint32_t bits = bm[w];
+        pre[w] = (uint16_t)r;
+        r += __popc(bits);
+        while (bits) {
+          const int q = __ffs(bits) - 1;
+          bits &= bits - 1;
+          pair_u[o] = (w << 5) + q;
+          pair_v[o] = v;
+          ++o;
+        }
+      }
+      __syncthreads();
+      if (tid == 0) s_carry = carry + tot;
+    }
+    __syncthreads();
+    // ---- 4. score: second walk, one integer RED per 2-path that lands on a candidate ----
+    ScoreVisitor<HAS_W, WANT_CN> sv{bm, blk, pre, wtable, HAS_W ? acc + out_base : nullptr,
+                                    WANT_CN ? cn + out_base : nullptr};
+    walk_two_paths(rowptr, col, vs, ve, warp, NW, lane, sv);
+    __syncthreads();
+    // ---- 5. cleanup ----
+    for (int c = 0; c < W2; c += TS_THREADS) {
+      const int g = c + tid;
+      if (g < W2) {
+        uint32_t m = bm2[g];
+        while (m) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          bm[g * 32 + b] = 0;
+        }
+        bm2[g] = 0;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+twohop_finalize_kernel(const unsigned long long *__restrict__ acc, const int *__restrict__ cn,
+                       long long N, int flags, float *__restrict__ score) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+    float sc = acc ? from_fixed(acc[i]) : (float)cn[i];
+    if (flags & EPS_CN_SIGMOID) sc = sigmoidf_ref(sc);
+    score[i] = sc;
+  }
+}
+
+}  // namespace eps
+
+extern "C" size_t eps_twohop_scored_workspace_bytes(int64_t N) {
+  return 256 + (size_t)(N > 0 ? N : 0) * 8;
+}
+
+extern "C" int eps_twohop_scored(const int32_t *rowptr, const int32_t *col, const float *wtable,
+                                 int32_t n, int32_t v_lo, int32_t v_hi, const int64_t *offsets,
+                                 int64_t N, int flags, int32_t *pair_u, int32_t *pair_v, float *score,
+                                 int32_t *count, void *workspace, size_t workspace_bytes,
+                                 void *stream_) {
+  using namespace eps;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EPS_CHECK_ARG(rowptr && col && offsets, "null graph or offsets pointer");
+  EPS_CHECK_ARG(n > 0 && v_lo >= 0 && v_hi <= n && v_lo <= v_hi && N >= 0, "bad owner range or N");
+  if (v_lo == v_hi || N == 0) return EPS_OK;
+  EPS_CHECK_ARG(pair_u && pair_v && (score || count), "missing output pointer");
+  const int sms = sm_count();
+  if (sms <= 0) { set_error("eps_twohop_scored: no CUDA device"); return EPS_ERR_CUDA; }
+  if (!workspace || workspace_bytes < eps_twohop_scored_workspace_bytes(N)) {
+    set_error("eps_twohop_scored: workspace too small");
+    return EPS_ERR_WORKSPACE;
+  }
+  const int W = (n + 31) / 32, W2 = (W + 31) / 32;
+  const size_t smem = (size_t)(W + 2 * W2) * 4 + (size_t)W * 2 + 16;
+  if (smem > 200 * 1024) {
+    set_error("eps_twohop_scored: n=%d needs %zu bytes of shared memory (> 200 KB)", n, smem);
+    return EPS_ERR_UNSUPPORTED;
+  }
+  unsigned long long *acc = nullptr;
+  int *cn = count;
+  uint8_t *ws = (uint8_t *)workspace;
+  EPS_CUDA(cudaMemsetAsync(ws, 0, 4, stream));
+  if (wtable) {
+    acc = (unsigned long long *)(ws + 256);
+    EPS_CUDA(cudaMemsetAsync(acc, 0, (size_t)N * 8, stream));
+  } else if (!cn) {
+    cn = (int *)(ws + 256);          // CN scores only: count lives in the workspace
+  }
+  if (cn) EPS_CUDA(cudaMemsetAsync(cn, 0, (size_t)N * 4, stream));
+  void (*kern)(const int *, const int *, const float *, int, int, int, const long long *, int *, int *,
+               unsigned long long *, int *, unsigned int *);
+  if (wtable) kern = cn ? twohop_score_kernel<true, true> : twohop_score_kernel<true, false>;
+  else kern = twohop_score_kernel<false, true>;
+  EPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  EPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TS_THREADS, smem));
+  if (occ < 1) occ = 1;
+  const int grid = (int)std::min<long long>((long long)(v_hi - v_lo), (long long)sms * occ);
+  kern<<<grid, TS_THREADS, smem, stream>>>(rowptr, col, wtable, n, v_lo, v_hi,
+                                           (const long long *)offsets, pair_u, pair_v, acc, cn,
+                                           (unsigned int *)ws);
+  EPS_LAUNCH_CHECK();
+  if (score) {
+    const int fgrid = (int)std::min<long long>((N + 255) / 256, (long long)sms * 8);
+    twohop_finalize_kernel<<<fgrid, 256, 0, stream>>>(acc, cn, (long long)N, flags, score);
+    EPS_LAUNCH_CHECK();
+  }
+  return EPS_OK;
+}

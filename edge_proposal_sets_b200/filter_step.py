@@ -46,6 +46,31 @@ def score_edges(model_name: str, model, x, adj: SparseAdj, edges: torch.Tensor,
     raise ValueError(f"model {model_name!r} is not a filter model on this path")
 
 
+def same_structure(a: SparseAdj, b: SparseAdj) -> bool:
+    """True when two unweighted adjacencies hold the same entries (e.g. the RA graph rebuilt from
+    the raw train split, filter.py:130-139, when no proposal edges were added)."""
+    return (a is b) or (a.val is None and b.val is None and a.n == b.n and a.nnz == b.nnz
+                        and bool(torch.equal(a.rowptr, b.rowptr)) and bool(torch.equal(a.col, b.col)))
+
+
+def heuristic_table(model_name: str, adj: SparseAdj, ra_adj: Optional[SparseAdj] = None):
+    """(graph, weight table, sigmoid) of a heuristic filter model when it can take the fused
+    enumerate+score kernel (K6+K3, candidates.two_hop_scored): unweighted adjacency, and the scoring
+    graph IS the graph whose 2-hop neighbourhood defines the candidates.  ``None`` otherwise
+    (collab's weighted adjacency, RA on a rebuilt multigraph) -> two_hop + ops.cn_aa."""
+    if adj.val is not None:
+        return None
+    if model_name == "simple":
+        return adj, None, False                              # models.py:536-542
+    if model_name == "adamic":
+        return adj, adj.adamic_weights(), True               # models.py:544-554
+    if model_name == "adamic_ogb":
+        return adj, adj.aa_ogb_weights(), False              # adamic_utils.py:13-25
+    if model_name == "resource_allocation" and (ra_adj is None or same_structure(ra_adj, adj)):
+        return adj, adj.ra_weights(), False                  # train_and_eval.py:195-216
+    return None
+
+
 def ra_graph_from_train_edges(train_edges: torch.Tensor, num_nodes: int) -> SparseAdj:
     """filter.py:130-139: A rebuilt from the raw train split, both directions, duplicate pairs
     SUMMED into integer weights (scipy csr_matrix constructor semantics)."""
@@ -105,13 +130,20 @@ def filter_topk(model_name: str, model, x, adj: SparseAdj, k: Optional[int] = No
         v_lo, v_hi = bounds[rank], bounds[rank + 1]
     running = None
     n_scored = 0
+    fused = heuristic_table(model_name, adj, ra_adj) if model_name not in GNN_MODELS else None
     for lo, hi, counts in iter_slabs(adj, v_lo, v_hi, slab_pairs):
-        edges = candidates.two_hop(adj, lo, hi, counts)
+        if fused is not None:
+            # CN / AA / RA are the values of A@A: one walk over the owners' 2-paths yields the
+            # candidates and their scores together (bit-identical to scoring the pairs with K3)
+            edges, score = candidates.two_hop_scored(fused[0], fused[1], lo, hi, counts, sigmoid=fused[2])
+        else:
+            edges = candidates.two_hop(adj, lo, hi, counts)
         M = edges.shape[1]
         if M == 0:
             continue
         n_scored += M
-        score = score_edges(model_name, model, x, adj, edges, True, ra_adj)
+        if fused is None:
+            score = score_edges(model_name, model, x, adj, edges, True, ra_adj)
         kk = M if k is None else min(k, M)
         top = ops.topk_edges(edges, score, kk)
         running = top if running is None else _merge_running(running, top, (running.shape[0] + kk) if k is None else k)

@@ -105,10 +105,10 @@ def linkpred_mlp(h: torch.Tensor, edges: torch.Tensor, weights: Sequence[torch.T
     Wp = (C.c_void_p * L)(*[w.data_ptr() for w in Ws])
     bp = (C.c_void_p * L)(*[b.data_ptr() for b in bs])
     score = torch.empty(M, dtype=torch.float32, device=h.device)
-    ws = _ws(lib.eps_linkpred_workspace_bytes(H, L, prec), h.device)
+    ws = _ws(lib.eps_linkpred_workspace_bytes(n, H, L, M, prec), h.device)
     check(lib.eps_linkpred_mlp(_ptr(h), n, H, _ptr(pu), _ptr(pv), M, Wp, bp, L, prec, int(sigmoid),
                                _ptr(score), _ptr(ws), ws.numel(), _stream()), "eps_linkpred_mlp")
-    LAUNCHES["n"] += (2 if prec == EPS_MLP_TC_BF16 else 1) if M else 0
+    LAUNCHES["n"] += ((3 if M >= 2 * n else 2) if prec == EPS_MLP_TC_BF16 else 1) if M else 0
     return score
 
 

@@ -87,7 +87,10 @@ int eps_gcn_norm_fill(const int32_t *rowptr, const int32_t *col, const float *va
  *           (/root/reference/adamic_utils.py:13-25) and
  *           train_and_eval.resource_allocation
  *           (/root/reference/train_and_eval.py:195-216).
- *   score[i] = sum_{k in N(u_i) & N(v_i)} a_u * (a_v * w_k)      (k ascending, fp32)
+ *   score[i] = RN_fp32( sum_{k in N(u_i) & N(v_i)} t_k ),  t_k = a_u * (a_v * w_k) in fp32;
+ *              the t_k are added EXACTLY (64-bit fixed point, 38 fractional bits: exact for
+ *              |t_k| >= 2^-15, <= 2^-39 absolute error per smaller term; |sum| < 2^25), so a
+ *              score depends on (graph, u, v) only - not on order, batch, grid or GPU count
  *     a_u = val[u,k], a_v = val[v,k]  (1 when val == NULL)
  *     w_k = wtable[k]                 (1 when wtable == NULL -> plain CN)
  *   count[i] = |N(u_i) & N(v_i)|  (int32, exact)
@@ -124,7 +127,7 @@ int eps_linkpred_mlp(const float *h, int32_t n, int32_t H, const int32_t *pair_u
                      const int32_t *pair_v, int64_t M, const float *const *W_h,
                      const float *const *b_h, int32_t L, int precision, int apply_sigmoid,
                      float *score, void *workspace, size_t workspace_bytes, void *stream);
-size_t eps_linkpred_workspace_bytes(int32_t H, int32_t L, int precision);
+size_t eps_linkpred_workspace_bytes(int32_t n, int32_t H, int32_t L, int64_t M, int precision);
 
 /* ---------------------------------------------------------------------------
  * K4  top-k proposal selection
@@ -165,6 +168,31 @@ int eps_twohop_candidates(const int32_t *rowptr, const int32_t *col, int32_t n, 
                           int32_t v_hi, const int64_t *offsets, uint32_t *counts, int32_t *pair_u,
                           int32_t *pair_v, void *workspace, size_t workspace_bytes, void *stream);
 size_t eps_twohop_workspace_bytes(void);
+
+/* ---------------------------------------------------------------------------
+ * K6+K3 fused  2-hop candidates of [v_lo, v_hi) TOGETHER WITH their CN / AA / RA
+ * scores, from one walk over the 2-paths of each owner.
+ * replaces: filter.py:96-109 (A@A enumeration, values discarded at :108-109)
+ *           + the scoring loop filter.py:113-142 for the heuristic models
+ *           (models.py:536-554, adamic_utils.py:13-25,
+ *           train_and_eval.py:195-216).
+ * A2's values ARE the scores: each 2-path v-k-u adds 1 (CN) or wtable[k]
+ * (AA: 1/log deg, RA: 1/deg) to candidate (u, v).  Sums are accumulated as
+ * 64-bit fixed-point integers with atomics (exact, order-independent), so
+ * score[i] == eps_cn_aa's score of the same pair, bit for bit.
+ *   offsets  int64[v_hi - v_lo + 1] exclusive prefix of the per-owner counts
+ *            returned by eps_twohop_candidates' count pass; N = offsets[last]
+ *   wtable   NULL -> score = CN count; else score = sum of wtable[k]
+ *   flags    EPS_CN_SIGMOID
+ *   score    fp32[N] or NULL;  count int32[N] or NULL (exact CN)
+ * Unweighted adjacency only (weighted graphs: eps_twohop_candidates + eps_cn_aa).
+ * Needs ~3n/16 bytes of shared memory (<= 200 KB, i.e. n <= ~1.0M).
+ * ------------------------------------------------------------------------- */
+int eps_twohop_scored(const int32_t *rowptr, const int32_t *col, const float *wtable, int32_t n,
+                      int32_t v_lo, int32_t v_hi, const int64_t *offsets, int64_t N, int flags,
+                      int32_t *pair_u, int32_t *pair_v, float *score, int32_t *count,
+                      void *workspace, size_t workspace_bytes, void *stream);
+size_t eps_twohop_scored_workspace_bytes(int64_t N);
 
 /* ---------------------------------------------------------------------------
  * K5  multi-GPU merge of per-GPU proposal lists (no counterpart in the

@@ -91,9 +91,12 @@ def _seq_fp32_segment_sum(pair: np.ndarray, terms: np.ndarray, B: int, order: st
                         (``_minor_reduce``), i.e. bit-for-bit what the reference computes: numpy
                         evaluates t0 + (t1 + t2 + ...) and switches to an 8-way unrolled pairwise
                         scheme inside the bracket from 8 terms on.
-    order="sequential"  strict left fold ((t0 + t1) + t2) + ... in fp32 — the order the CUDA
-                        kernels implement; identical bits to "numpy" up to 2 terms, within a few
-                        ulp (measured <= 2.8e-7 relative on twitch) beyond.
+    order="sequential"  strict left fold ((t0 + t1) + t2) + ... in fp32; identical bits to
+                        "numpy" up to 2 terms, within a few ulp beyond.
+    order="exact"       what the CUDA kernels compute (include/eps.h, K3 and K6+K3): every fp32 term
+                        becomes the integer RN(t * 2^38), the integers are added exactly, and the sum
+                        is rounded ONCE to fp32 — order-independent; for terms >= 2^-15 it is the
+                        correctly rounded exact sum (measured <= 2.4e-7 relative from "numpy" on twitch).
     """
     out = np.zeros(B, dtype=np.float32)
     if pair.size == 0:
@@ -104,6 +107,13 @@ def _seq_fp32_segment_sum(pair: np.ndarray, terms: np.ndarray, B: int, order: st
     if order == "numpy":
         out[pair[starts]] = np.add.reduceat(terms, starts)
         return out
+    if order == "exact":
+        fx = np.rint(terms.astype(np.float64) * float(1 << FX_FRAC_BITS)).astype(np.int64)   # exact: 24-bit x 2^38
+        sums = np.add.reduceat(fx, starts)
+        assert np.all(np.abs(sums) < (1 << 53)), "oracle: fixed-point sum beyond exact float64 range"
+        # int64 -> float64 exact below 2^53, float64 -> float32 is ONE round-to-nearest-even
+        out[pair[starts]] = (sums.astype(np.float64) * 2.0 ** -FX_FRAC_BITS).astype(np.float32)
+        return out
     lens = np.diff(np.concatenate([starts, [pair.size]]))
     acc = terms[starts].copy()
     for j in range(1, int(lens.max())):
@@ -111,6 +121,9 @@ def _seq_fp32_segment_sum(pair: np.ndarray, terms: np.ndarray, B: int, order: st
         acc[live] = (acc[live] + terms[starts[live] + j]).astype(np.float32)
     out[pair[starts]] = acc
     return out
+
+
+FX_FRAC_BITS = 38   # edge_proposal_sets_b200/csrc/eps_common.cuh EPS_FX_FRAC_BITS
 
 
 def _batched(fn, edges: np.ndarray, batch: int) -> np.ndarray:

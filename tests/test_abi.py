@@ -38,7 +38,8 @@ def test_argument_validation_needs_no_device():
     assert lib.eps_topk_f32(None, 10, 3, None, None, None, 0, None) == -1
     assert lib.eps_spmm_csr_f32(None, None, None, None, None, 4, 8, 0, None, 0, None, 0, None) == -1
     assert lib.eps_topk_workspace_bytes(1 << 20, 1000) > 0
-    assert lib.eps_linkpred_workspace_bytes(256, 3, 0) >= 256
+    assert lib.eps_linkpred_workspace_bytes(1000, 256, 3, 5000, 0) >= 256
+    assert lib.eps_linkpred_workspace_bytes(1000, 256, 3, 5000, 1) >= 256 + 2 * 256 * 256 * 2 + 1000 * 256 * 2
 
 
 def test_no_cpu_fallback():

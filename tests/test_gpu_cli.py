@@ -30,7 +30,7 @@ def test_filter_cli_adamic_ogb_then_rank_eval(tmp_path):
     z, ei, g = golden_graph("fb")
     cand = og.two_hop_candidates(g)
     assert f"using {cand.shape[1]} edges" in r.stdout
-    aa_seq = oh.aa_ogb_pairs(g, cand, order="sequential")
+    aa_seq = oh.aa_ogb_pairs(g, cand, order="exact")
     # device weight table (CUDA logf) vs numpy logf: scores agree to 1e-5 relative, so compare the
     # list through the oracle's scores of the SAME pairs and require a consistent ordering
     lookup = {(int(a), int(b)): i for i, (a, b) in enumerate(cand.T)}

@@ -1,7 +1,7 @@
 """K3 (CN / AA / RA) and K6 (candidate enumeration) on the GPU vs the oracle and the golden
-vectors produced by the reference itself.  Bit-exact for counts and — because the kernels fold
-terms left-to-right in ascending neighbour order like scipy's csr_matvec — for fp32 AA too when
-given the oracle's weight table; <=1e-5 relative with the device-computed table."""
+vectors produced by the reference itself.  Bit-exact for counts and — because the kernels add the
+fp32 terms exactly (64-bit fixed point) and round once, the oracle's order="exact" — for fp32 AA too
+when given the oracle's weight table; <=1e-5 relative against the reference's own outputs."""
 import hashlib
 
 import numpy as np
@@ -36,8 +36,8 @@ def test_sample_vs_reference_golden(gold, grouped):
     assert np.array_equal(score.cpu().numpy(), z["sample_cn"].astype(np.float32))
     w = _dev(oh.aa_ogb_weights(g))
     aa = ops.cn_aa(adj, e, w, grouped_by_v=grouped).cpu().numpy()
-    # bit-exact against the oracle's strict left fold (the kernels' summation order) ...
-    assert np.array_equal(aa, oh.aa_ogb_pairs(g, z["sample_edges"].astype(np.int64), order="sequential"))
+    # bit-exact against the oracle's exact-sum-rounded-once restatement (the kernels' contract) ...
+    assert np.array_equal(aa, oh.aa_ogb_pairs(g, z["sample_edges"].astype(np.int64), order="exact"))
     # ... and within the north_star tolerance of the reference's own output (numpy's reduceat
     # switches to pairwise summation for >= 9 common neighbours, so the last bits can differ)
     ref0 = z["sample_aa"]
@@ -104,7 +104,7 @@ def test_weighted_collab_graph():
         got = ops.cn_aa(adj, e, None, grouped_by_v=grouped).cpu().numpy()
         assert np.array_equal(got, oh.cn_scores_pairs(g, cand))                    # integer weights: exact in any order
         aa = ops.cn_aa(adj, e, _dev(oh.aa_ogb_weights(g)), grouped_by_v=grouped).cpu().numpy()
-        assert np.array_equal(aa, oh.aa_ogb_pairs(g, cand, order="sequential"))
+        assert np.array_equal(aa, oh.aa_ogb_pairs(g, cand, order="exact"))
         assert np.allclose(aa, oh.aa_ogb_pairs(g, cand), rtol=1e-5, atol=0)
     # random (ungrouped, repeated, self) pairs
     rng = np.random.default_rng(4)
@@ -128,7 +128,7 @@ def test_tiny_graphs_and_edge_cases():
         for grouped in (False, True):
             sc, cnt = ops.cn_aa(adj, _dev(cand), _dev(oh.aa_ogb_weights(g)), grouped_by_v=grouped, want_count=True)
             assert np.array_equal(cnt.cpu().numpy(), oh.cn_count_pairs(g, cand)), name
-            assert np.array_equal(sc.cpu().numpy(), oh.aa_ogb_pairs(g, cand, order="sequential")), name
+            assert np.array_equal(sc.cpu().numpy(), oh.aa_ogb_pairs(g, cand, order="exact")), name
     # all pairs incl. isolated nodes and (u,u)
     n, e = tiny_graphs()["mixed8"]
     g = csr_from_undirected(n, e)
@@ -153,3 +153,79 @@ def test_candidate_enumeration_vs_oracle(shape):
     assert torch.equal(torch.cat(parts, 1), got)
     counts = candidates.owner_counts(adj).cpu().numpy()
     assert np.array_equal(counts, np.bincount(cand[1], minlength=s["n"]))
+
+
+# ---------------------------------------------------------------------------------------------
+# K6+K3 fused: candidates and scores from one walk over the 2-paths
+# ---------------------------------------------------------------------------------------------
+
+def test_fused_twohop_scored_full_golden(gold):
+    """Full candidate set of twitch / fb: same list (sha256), CN / AA / RA bit-identical to K3 on the
+    enumerated pairs, checksums and the exact CN top-k list of the golden file."""
+    from edge_proposal_sets_b200 import candidates, ops
+    name, z, g, adj = gold
+    w = _dev(oh.aa_ogb_weights(g))
+    edges, aa, cnt = candidates.two_hop_scored(adj, w, want_count=True)
+    N = int(z["num_candidates"])
+    assert edges.shape == (2, N)
+    assert hashlib.sha256(edges.t().contiguous().t().cpu().numpy().tobytes()).hexdigest() == str(z["cand_sha256"])
+    assert int(cnt.long().sum()) == int(z["sum_cn"]) and int(cnt.max()) == int(z["max_cn"]) and int(cnt.min()) >= 1
+    aa3, cnt3 = ops.cn_aa(adj, edges, w, grouped_by_v=True, want_count=True)
+    assert torch.equal(cnt, cnt3) and torch.equal(aa, aa3)                         # fused == per-pair kernel, bit for bit
+    assert abs(float(aa.double().sum()) - float(z["sum_aa"])) <= 1e-7 * float(z["sum_aa"])
+    e2, cn_score = candidates.two_hop_scored(adj, None)
+    assert torch.equal(e2, edges) and torch.equal(cn_score, cnt.float())
+    e3, ra = candidates.two_hop_scored(adj, adj.ra_weights())
+    assert torch.equal(ra, ops.cn_aa(adj, edges, adj.ra_weights(), grouped_by_v=True))
+    e4, sg = candidates.two_hop_scored(adj, w, sigmoid=True)
+    assert torch.equal(sg, ops.cn_aa(adj, edges, w, sigmoid=True, grouped_by_v=True))
+    k = int(z["topk_k"])
+    uv = ops.topk_edges(edges, cn_score, k)[:, :2].to(torch.int32).cpu().numpy()
+    assert hashlib.sha256(np.ascontiguousarray(uv).tobytes()).hexdigest() == str(z["topk_cn_sha256"])
+    # the sampled pairs of the golden file: the reference's own AA within the north_star tolerance
+    pos = _dev(z["sample_index"])
+    assert np.array_equal(edges[:, pos].cpu().numpy(), z["sample_edges"])
+    got = aa[pos].cpu().numpy()
+    assert np.all(np.abs(got - z["sample_aa"]) <= 1e-5 * np.abs(z["sample_aa"]))
+    assert np.array_equal(cnt[pos].cpu().numpy(), z["sample_cn"])
+
+
+@pytest.mark.parametrize("shape", ["tiny", "small"])
+def test_fused_twohop_scored_vs_oracle(shape):
+    from edge_proposal_sets_b200 import candidates
+    s, ei, w, g = synth_graph(shape)
+    adj = to_adj(g, DEV)
+    cand = og.two_hop_candidates(g)
+    wt = oh.aa_ogb_weights(g)
+    edges, aa, cnt = candidates.two_hop_scored(adj, _dev(wt), want_count=True)
+    assert np.array_equal(edges.cpu().numpy(), cand.astype(np.int32))
+    assert np.array_equal(cnt.cpu().numpy(), oh.cn_count_pairs(g, cand))
+    assert np.array_equal(aa.cpu().numpy(), oh.aa_ogb_pairs(g, cand, order="exact"))
+    assert np.allclose(aa.cpu().numpy(), oh.aa_ogb_pairs(g, cand), rtol=1e-5, atol=0)   # reference (numpy) order
+    # owner-range slabs concatenate to the full result
+    mid = s["n"] // 3
+    a = candidates.two_hop_scored(adj, _dev(wt), 0, mid)
+    b = candidates.two_hop_scored(adj, _dev(wt), mid, s["n"])
+    assert torch.equal(torch.cat([a[0], b[0]], 1), edges) and torch.equal(torch.cat([a[1], b[1]]), aa)
+
+
+def test_fused_twohop_scored_tiny_graphs():
+    from edge_proposal_sets_b200 import candidates
+    for name, (n, e) in tiny_graphs().items():
+        g = csr_from_undirected(n, e)
+        adj = to_adj(g, DEV)
+        cand = og.two_hop_candidates(g)
+        edges, sc, cnt = candidates.two_hop_scored(adj, _dev(oh.aa_ogb_weights(g)), want_count=True)
+        assert np.array_equal(edges.cpu().numpy(), cand.astype(np.int32)), name
+        if cand.shape[1]:
+            assert np.array_equal(cnt.cpu().numpy(), oh.cn_count_pairs(g, cand)), name
+            assert np.array_equal(sc.cpu().numpy(), oh.aa_ogb_pairs(g, cand, order="exact")), name
+    # an empty owner range and a weighted graph (unsupported: must raise, not fall back)
+    s, ei, w, g = synth_graph("tiny")
+    adj = to_adj(g, DEV)
+    e0, s0 = candidates.two_hop_scored(adj, None, 5, 5)
+    assert e0.shape == (2, 0) and s0.numel() == 0
+    from edge_proposal_sets_b200._lib import EpsError
+    adjw = to_adj(g, DEV, keep_values=True)
+    with pytest.raises(EpsError):
+        candidates.two_hop_scored(adjw, None)

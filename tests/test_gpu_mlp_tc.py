@@ -23,7 +23,8 @@ def _setup(H, L, n, M, seed=0, scale=0.5):
 
 
 @pytest.mark.timeout(120)
-@pytest.mark.parametrize("H,L,M", [(256, 2, 128), (256, 2, 70001), (256, 3, 40000), (128, 3, 5000), (64, 2, 999)])
+@pytest.mark.parametrize("H,L,M", [(256, 2, 128), (256, 2, 70001), (256, 3, 40000), (128, 3, 5000), (64, 2, 999),
+                                   (64, 2, 150001), (128, 4, 120000), (256, 3, 9000)])
 def test_tc_arm_vs_oracle(H, L, M):
     from edge_proposal_sets_b200 import ops
     sd, h, e, Ws, bs = _setup(H, L, 5000, M)
@@ -42,14 +43,15 @@ def test_tc_arm_vs_oracle(H, L, M):
 
 @pytest.mark.timeout(120)
 def test_tc_arm_matches_bf16_rounded_oracle_tightly():
-    """With the oracle fed the SAME bf16-rounded operands the only difference left is fp32
-    accumulation order: the kernel must agree to ~1e-5, which pins layouts/descriptors exactly."""
+    """With the oracle fed the SAME bf16-rounded operands — bf16(bf16(h_u) * bf16(h_v)), the
+    kernels' first-layer A operand (tc_common.cuh) — the only difference left is fp32 accumulation
+    order: the kernel must agree to ~1e-5, which pins layouts/descriptors exactly."""
     from edge_proposal_sets_b200 import ops
     H, L, M = 256, 3, 20000
     sd, h, e, Ws, bs = _setup(H, L, 3000, M, seed=3)
     bf = lambda t: t.to(torch.bfloat16).to(torch.float64)
     ht = torch.from_numpy(h)
-    z = bf((ht[e[0]] * ht[e[1]]))
+    z = bf((bf(ht[e[0]]) * bf(ht[e[1]])).float())
     for i in range(L - 1):
         z = torch.relu(z @ bf(sd[f"linkpred.lins.{i}.weight"]).t() + sd[f"linkpred.lins.{i}.bias"].double())
         if i < L - 2:
@@ -73,3 +75,18 @@ def test_tc_arm_ranking_quality():
     overlap = len(top_tc & top_fp) / k
     print(f"top-{k} overlap bf16-vs-fp32 arm: {overlap:.4f}")
     assert overlap >= 0.97
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("H,L", [(256, 3), (256, 2), (128, 3), (64, 2)])
+def test_tc_arm_score_is_a_function_of_the_pair_only(H, L):
+    """Long pair lists gather from a bf16 copy of h, short ones read the fp32 rows and round them in
+    registers; tiles, clusters and ring stages differ too.  Same pair -> same bits, always."""
+    from edge_proposal_sets_b200 import ops
+    n, M = 3000, 40000                                   # M >= 2n: table path
+    sd, h, e, Ws, bs = _setup(H, L, n, M, seed=9)
+    hd, ed = torch.from_numpy(h).to(DEV), torch.from_numpy(e).to(DEV)
+    full = ops.linkpred_mlp(hd, ed, Ws, bs, "bf16", sigmoid=False)
+    for lo, hi in [(0, 5000), (12345, 12345 + 777), (M - 300, M)]:      # M' < 2n: fp32-source path
+        part = ops.linkpred_mlp(hd, ed[:, lo:hi].contiguous(), Ws, bs, "bf16", sigmoid=False)
+        assert torch.equal(part, full[lo:hi])
