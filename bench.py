@@ -38,7 +38,9 @@ def parse():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--workload", default="ppa", choices=["ppa", "collab", "ddi", "small", "tiny"])
-    p.add_argument("--pairs", type=int, default=1 << 26, help="target candidates per slab per GPU")
+    p.add_argument("--pairs", type=int, default=1 << 26, help="target candidates per owner slab")
+    p.add_argument("--slabs", type=int, default=4,
+                   help="owner slabs per step per GPU (the GCN embeddings are computed once per step)")
     p.add_argument("--mlp", default=None, choices=[None, "fp32", "bf16"],
                    help="K2 arm: bf16 = tcgen05 tensor-core kernel (default), fp32 = FFMA parity arm")
     p.add_argument("--scale", type=float, default=1.0, help="shrink the synthetic graph (debug only)")
@@ -335,53 +337,81 @@ def run_b200(args):
 
     adj, x, model, _ready = upload()
     torch.cuda.synchronize()
-    # ---- choose this rank's owner slab (weak scaling: slab r of ~args.pairs candidates) ----
+    # ---- this rank's owner range: `--slabs` consecutive slabs of ~`--pairs` candidates (weak scaling) ----
     counts = candidates.owner_counts(adj).cpu().numpy()
     cum = np.cumsum(counts)
-    lo = 0
-    for r in range(rank + 1):
-        lo, hi = choose_slab(cum, lo, args.pairs)
-        if r < rank:
-            lo = hi
-    lo, hi = choose_slab(cum, lo, args.pairs)
     n_total_candidates = int(cum[-1])
-    slab_pairs = int(cum[hi - 1] - (cum[lo - 1] if lo else 0))
-    k = 4_000_000 if slab_pairs >= 16_000_000 else max(slab_pairs // 8, 1)
+    lo = 0
+    slabs = []
+    for i in range((rank + 1) * args.slabs):
+        if lo >= n:
+            break
+        lo, hi = choose_slab(cum, lo, args.pairs)
+        if i >= rank * args.slabs:
+            slabs.append((lo, hi))
+        lo = hi
+    assert slabs, "graph too small for this many ranks x slabs x pairs"
+    slab_sizes = [int(cum[b - 1] - (cum[a - 1] if a else 0)) for a, b in slabs]
+    M = sum(slab_sizes)
+    k = 4_000_000 if M >= 16_000_000 else max(M // 8, 1)
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    phases = ["candgen", "cn_aa", "embed", "mlp", "topk", "merge"]
+    phases = ["embed", "candgen", "cn_aa", "mlp", "topk", "merge"]
 
     def step(adj, x, model, record=None, weights_ready=None):
-        """One filter step on resident inputs.  Returns the two [k,3] proposal lists."""
-        marks = [ev() for _ in range(len(phases) + 1)] if record is not None else None
-        if marks: marks[0].record()
+        """One filter step on resident inputs: embeddings once, then every owner slab of this rank
+        is enumerated, scored by both filter models and folded into the two running top-k lists
+        (filter_step.filter_topk's loop).  Returns the two [k,3] proposal lists."""
+        rec = record is not None
+        marks = []
+        mark = (lambda: (marks.append(ev()), marks[-1].record())) if rec else (lambda: None)
         adj._cache.clear()                                    # nothing derived from the graph is reused
-        cnt = candidates.owner_counts(adj, lo, hi)             # K6 count pass (sizes the slab)
-        if marks: marks[1].record()
-        aa_w = adj.aa_ogb_weights()
-        if adj.val is None and not args.unfused:
-            # K6+K3 fused: candidates + AA score + exact CN count from one walk over the 2-paths
-            edges, aa, cn = candidates.two_hop_scored(adj, aa_w, lo, hi, cnt, want_count=True)
-        else:
-            edges = candidates.two_hop(adj, lo, hi, cnt)
-            aa, cn = ops.cn_aa(adj, edges, aa_w, use_values=adj.val is not None, grouped_by_v=True, want_count=True)
-        if marks: marks[2].record()
+        model._h_key = None                                   # no caching across steps
+        mark()
         if weights_ready is not None:
             torch.cuda.current_stream().wait_event(weights_ready)
-        model._h_key = None                                   # no caching across steps
-        hemb = model.embed(x, adj)                            # gcn_norm + 3 x (GEMM + SpMM)
-        if marks: marks[3].record()
-        sc = model.linkpred.score_pairs(hemb, edges)
-        if marks: marks[4].record()
-        top_aa = ops.topk_edges(edges, aa, k)
-        top_nn = ops.topk_edges(edges, sc, k)
-        if marks: marks[5].record()
+        hemb = model.embed(x, adj)                            # gcn_norm + L x (GEMM + SpMM)
+        aa_w = adj.aa_ogb_weights()
+        mark()
+        run_aa = run_nn = None
+        for (a, b) in slabs:
+            cnt = candidates.owner_counts(adj, a, b)          # K6 count pass (sizes the slab)
+            mark()
+            if adj.val is None and not args.unfused:
+                # K6+K3 fused: candidates + AA score + exact CN count from one walk over the 2-paths
+                edges, aa, cn = candidates.two_hop_scored(adj, aa_w, a, b, cnt, want_count=True)
+            else:
+                edges = candidates.two_hop(adj, a, b, cnt)
+                aa, cn = ops.cn_aa(adj, edges, aa_w, use_values=adj.val is not None, grouped_by_v=True, want_count=True)
+            mark()
+            sc = model.linkpred.score_pairs(hemb, edges)
+            mark()
+            kk = min(k, edges.shape[1])
+            top_aa = ops.topk_edges(edges, aa, kk)
+            top_nn = ops.topk_edges(edges, sc, kk)
+            run_aa = filter_step._merge_running(run_aa, top_aa, k)
+            run_nn = filter_step._merge_running(run_nn, top_nn, k)
+            mark()
+            del edges, aa, cn, sc
         if world > 1:
-            top_aa = parallel.merge_topk(top_aa, k)
-            top_nn = parallel.merge_topk(top_nn, k)
-        if marks:
-            marks[6].record()
+            run_aa = parallel.merge_topk(run_aa, k)
+            run_nn = parallel.merge_topk(run_nn, k)
+        mark()
+        if rec:
             record.append(marks)
-        return top_aa, top_nn, edges.shape[1]
+        return run_aa, run_nn, M
+
+    def phase_times(marks):
+        """marks: [start, embed_end, (count_end, score_end, mlp_end, topk_end) x slabs, merge_end]"""
+        t = dict.fromkeys(phases, 0.0)
+        t["embed"] = marks[0].elapsed_time(marks[1])
+        prev = marks[1]
+        for s_ in range(len(slabs)):
+            for j, ph in enumerate(["candgen", "cn_aa", "mlp", "topk"]):
+                cur = marks[2 + 4 * s_ + j]
+                t[ph] += prev.elapsed_time(cur)
+                prev = cur
+        t["merge"] = prev.elapsed_time(marks[-1])
+        return t
 
     out_host = [torch.empty((k, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
 
@@ -393,17 +423,29 @@ def run_b200(args):
         torch.cuda.current_stream().synchronize()             # the caller holds the result on the host
         return out_host, M
 
-    # ---- algorithmic bytes of the K3 launch (4(d_u+d_v)+12 per pair) ----
-    cnt0 = candidates.owner_counts(adj, lo, hi)
-    edges0 = candidates.two_hop(adj, lo, hi, cnt0)
+    # ---- algorithmic work per step ----
     deg = adj.degree().long()
     per_pair = 8 if adj.val is not None else 4
-    k3_bytes = int((per_pair * (deg[edges0[0].long()] + deg[edges0[1].long()]) + 12).sum().item())
-    mean_du_dv = float((deg[edges0[0].long()] + deg[edges0[1].long()]).double().mean().item())
-    M = edges0.shape[1]
-    del edges0, cnt0
+    k3_bytes, sum_dudv = 0, 0.0
+    for (a, b) in slabs:
+        cnt0 = candidates.owner_counts(adj, a, b)
+        edges0 = candidates.two_hop(adj, a, b, cnt0)
+        dd = deg[edges0[0].long()] + deg[edges0[1].long()]
+        k3_bytes += int((per_pair * dd + 12).sum().item())   # 4(d_u+d_v)+12 per pair
+        sum_dudv += float(dd.double().sum().item())
+        assert edges0.shape[1] == slab_sizes[slabs.index((a, b))]
+        del edges0, cnt0, dd
+    mean_du_dv = sum_dudv / M
+    # the fused K6+K3 kernel walks the owners' 2-paths twice (mark, score) instead of two lists per
+    # pair: 2 x 4 B per 2-path + 4 B per N(v) entry x 3 + per candidate 8 B pair + 8 B fixed-point
+    # accumulator (zero, RED, read) + 4 B count + 4 B score out
+    work = candidates.two_path_work(adj)
+    twopaths = int(sum(int(work[a:b].sum().item()) for a, b in slabs))
+    fused_bytes = 8 * twopaths + 28 * M
     mlp_flops = M * (2 * H * H * (L - 1) + 3 * H)
     mlp_bytes = M * (2 * H * 4 + 12)
+    nnz_hat = int(h_col.numel()) + n                          # GCN adds the self loops
+    spmm_bytes = 4 * (n + 1) + 8 * nnz_hat + 4 * H * nnz_hat + 4 * n * H   # gather model, per layer
 
     def barrier():
         if world > 1:
@@ -418,6 +460,7 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     rec = []
+    ops.KERNEL_EVENTS = {}
     barrier()
     t_start, t_end = ev(), ev()
     t_start.record()
@@ -425,13 +468,16 @@ def run_b200(args):
         step(adj, x, model, rec)
     t_end.record()
     barrier()
+    kev, ops.KERNEL_EVENTS = ops.KERNEL_EVENTS, None
+    spmm_ms = [a_.elapsed_time(b_) for a_, b_ in kev.get("spmm_csr", [])]
     launches = ops.LAUNCHES["n"]
     ms_total = t_start.elapsed_time(t_end)
     tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_step = float(tmax.item()) / args.steps
-    phase_ms = {p: float(np.mean([m[i].elapsed_time(m[i + 1]) for m in rec])) for i, p in enumerate(phases)}
+    pt = [phase_times(m) for m in rec]
+    phase_ms = {p: float(np.mean([t[p] for t in pt])) for p in phases}
 
     # ---- end to end through the public API with HOST buffers ----
     for _ in range(2):
@@ -465,32 +511,56 @@ def run_b200(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         tc_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-        dom = max(["cn_aa", "mlp"], key=lambda p: phase_ms[p])
-        if dom == "cn_aa":
-            ach = k3_bytes / (phase_ms["cn_aa"] * 1e-3) / 1e9
-            roof = {"kernel": "cn_grouped_kernel (K3)", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
-                    "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": k3_bytes, "ms_per_launch": phase_ms["cn_aa"]}
-        else:
-            if mlp_arm == "fp32":
-                ach = mlp_bytes / (phase_ms["mlp"] * 1e-3) / 1e9
-                roof = {"kernel": "linkpred_fp32_kernel (K2 fp32 arm, FFMA-bound)", "bound": "hbm", "achieved": ach,
-                        "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
-                        "peak_source": peak_src, "algorithmic_bytes_per_launch": mlp_bytes,
-                        "ms_per_launch": phase_ms["mlp"]}
-            else:
-                ach = mlp_flops / (phase_ms["mlp"] * 1e-3) / 1e12
-                roof = {"kernel": "linkpred_tc_kernel (K2 tcgen05)", "bound": "tensor", "achieved": ach,
-                        "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak, "traffic": None,
-                        "peak_source": peak_src, "algorithmic_flops_per_launch": mlp_flops,
-                        "ms_per_launch": phase_ms["mlp"]}
+        S = len(slabs)
+        # ncu --set full DRAM traffic per launch of the same command (profiles/, one capture per round)
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {})
+        except Exception:
+            pass
+
+        def roof_entry(kernel, bound, work, ms, launches_, tkey, note=None):
+            peak = hbm_peak if bound == "hbm" else tc_peak
+            ach = work / launches_ / (ms / launches_ * 1e-3) / (1e9 if bound == "hbm" else 1e12)
+            e = {"kernel": kernel, "bound": bound, "achieved": ach, "peak": peak,
+                 "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": ach / peak,
+                 "traffic": traffic.get(tkey), "peak_source": peak_src,
+                 ("algorithmic_bytes_per_launch" if bound == "hbm" else "algorithmic_flops_per_launch"): work / launches_,
+                 "ms_per_launch": ms / launches_, "launches_per_step": launches_}
+            if note:
+                e["note"] = note
+            return e
+
+        fused = adj.val is None and not args.unfused
+        roofs = {
+            "mlp": roof_entry("linkpred_fp32_kernel (K2 fp32 arm, FFMA-bound)", "hbm", mlp_bytes, phase_ms["mlp"], S, "mlp_fp32")
+            if mlp_arm == "fp32" else
+            roof_entry("linkpred_tc3_kernel (K2 tcgen05, cta_group::2)", "tensor", mlp_flops, phase_ms["mlp"], S, "linkpred_tc3",
+                       "phase = bf16 table conversion + weight packing + the kernel"),
+            "cn_aa": roof_entry("twohop_score_kernel (K6+K3 fused)" if fused else "cn_grouped_kernel (K3)", "hbm",
+                                k3_bytes, phase_ms["cn_aa"], S, "twohop_score" if fused else "cn_grouped",
+                                "algorithmic bytes = the pair-by-pair figure 4(d_u+d_v)+12 of SURVEY 8d; the fused kernel "
+                                f"walks 2-paths instead and moves ~{fused_bytes / S / 1e9:.2f} GB per launch "
+                                f"({fused_bytes / S / (phase_ms['cn_aa'] / S * 1e-3) / 1e9:.0f} GB/s of its own traffic model)"
+                                if fused else None),
+        }
+        dom = max(roofs, key=lambda p: phase_ms[p])
+        roof = roofs[dom]
+        other = [roofs[p] for p in roofs if p != dom]
+        if spmm_ms:
+            per_step = len(spmm_ms) // args.steps
+            other.append(roof_entry("spmm_csr_kernel (K1)", "hbm", spmm_bytes * per_step,
+                                    float(np.sum(spmm_ms)) / args.steps, per_step, "spmm_csr",
+                                    "gather model 4(n+1)+8nnz+4F*nnz+4nF (SURVEY 8d); rows that hit in L2 let it exceed the HBM peak"))
         line = {
             "metric": "candidate pairs scored/sec (CN/AA + GCN+LinkPredictor filter step)",
             "value": total_pairs / (ms_step * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if mlp_arm == "fp32" else "bf16(mlp)/f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}-shape filter step: one owner slab per GPU, scored by AA(+CN) and GCN+LinkPredictor, top-{k} each",
-                       "n": n, "nnz": int(h_col.numel()), "candidates_per_gpu": M, "owners": [lo, hi],
+            "config": {"workload": f"{args.workload}-shape filter step: GCN embeddings once, then {len(slabs)} owner slab(s) per GPU enumerated, "
+                                   f"scored by AA(+CN) and GCN+LinkPredictor, running top-{k} each",
+                       "n": n, "nnz": int(h_col.numel()), "candidates_per_gpu": M, "slabs_per_gpu": len(slabs),
+                       "slab_candidates": slab_sizes, "owners": [slabs[0][0], slabs[-1][1]],
                        "graph_total_candidates": n_total_candidates, "mean_du_plus_dv": mean_du_dv,
                        "gnn": f"gcn L={L} H={H} F_in={H + host['feat']}", "mlp_arm": mlp_arm, "k": k,
                        "l2": "inputs larger than L2 (pairs+embeddings+CSR > 126 MB); no flush needed"
@@ -501,6 +571,7 @@ def run_b200(args):
                        "candgen_pairs_per_s": M / (phase_ms["candgen"] * 1e-3),
                        "topk_ms": phase_ms["topk"], "embed_ms": phase_ms["embed"]},
             "roofline": roof,
+            "roofline_other": other,
             "e2e": {"value": total_pairs * args.steps / (float(tm.item()) * 1e-3), "unit": "pairs/s",
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": launches,

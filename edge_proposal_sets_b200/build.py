@@ -46,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for src in sources():
         obj = os.path.join(HERE, "build", os.path.basename(src) + ".o")
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", src, "-o", obj]
+        cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("EPS_EXTRA_NVCC_FLAGS", "").split(), "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     log = []

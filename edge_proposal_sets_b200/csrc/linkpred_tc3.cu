@@ -19,7 +19,11 @@
 // The two accumulator slots let the tensor pipe start the next GEMM (next layer, or next tile's first
 // layer) while the epilogue drains the previous one; the ring decouples the HBM/L2 gather from both.
 #include <cooperative_groups.h>
+#include <stdio.h>
 #include <stdlib.h>
+
+#include <algorithm>
+#include <vector>
 
 #include "tc_common.cuh"
 
@@ -35,6 +39,9 @@ constexpr int P_IDS_WARP = P_EPI_WARPS + 1;                        // warp 5 pre
 constexpr int P_FIRST_PROD_WARP = P_EPI_WARPS + 2;
 // NG producer groups of four warps each: 3 -> 576 threads (96 registers), 2 -> 448 threads (144 registers)
 constexpr int p_threads(int ng) { return (P_EPI_WARPS + 2 + ng * P_GROUP_WARPS) * 32; }
+// one CTA per SM: the whole register file is there to be used
+// (16384 registers per SM sub-partition, warps dealt round-robin: 18 warps -> 5 on one -> 96; 14 -> 4 -> 128)
+constexpr int p_maxreg(int ng) { return (16384 / (((p_threads(ng) / 32) + 3) / 4) / 32) / 8 * 8; }
 constexpr int P_CHUNK_K = 32;
 constexpr int P_STAGE_BYTES = TC_BM * P_CHUNK_K * 2;               // 8 KB
 
@@ -46,6 +53,43 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw64(uint32_t saddr) {
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)4 << 61;                          // SWIZZLE_64B
   return d;
+}
+// 16-wide K tiles (one UMMA K step, 32-byte rows) in K-major SWIZZLE_32B: 8-row groups 256 B apart,
+// 16-byte chunk index ^= bit 7 of the byte offset = (r >> 2) & 1
+__device__ __forceinline__ uint64_t umma_smem_desc_sw32(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256u >> 4) << 32;                // 8 rows x 32 B
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;                          // SWIZZLE_32B
+  return d;
+}
+__device__ __forceinline__ uint32_t sw32_chunk_off(int r, int chunk) {
+  return (uint32_t)r * 32u + (uint32_t)((chunk ^ ((r >> 2) & 1)) << 4);
+}
+// tcgen05.ld of 32 accumulator columns WITHOUT the wait, and a wait that names the destination
+// registers so no use of them can be scheduled above it: the epilogue keeps the next chunk's load in
+// flight while it converts the current one.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t *r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t *r) {
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;\n"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+        "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+        "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+        "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+      :: "memory");
 }
 __device__ __forceinline__ uint32_t sw64_chunk_off(int r, int sub) {
   return (uint32_t)r * 64u + (uint32_t)((sub ^ ((r >> 1) & 3)) << 4);
@@ -76,6 +120,35 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t saddr, uint32_t parit
       "bra LAB_WAIT;\n\t"
       "DONE:\n\t}\n"
       :: "r"(saddr), "r"(parity) : "memory");
+}
+
+// Optional timeline trace of cluster 0 (build with -DEPS_TC3_TRACE; tools/tc3_trace.py reads the dump):
+// one record per pipeline event = tag | a | b | clock64 of the leader CTA's SM.
+#ifdef EPS_TC3_TRACE
+// fire-and-forget stores into a per-role region (MMA issuer 0, epilogue 1, producer group g 2+g); no atomics
+constexpr unsigned TR_REGION = 1u << 15;
+__device__ unsigned long long g_trace[8 * TR_REGION];
+#define TR_DECL(role) unsigned tr_n_ = 0; const unsigned tr_base_ = (unsigned)(role) * TR_REGION
+#define TR(tag, a, b)                                                                                  \
+  do {                                                                                                 \
+    if (cluster_id == 0 && cta_rank == 0 && tr_n_ < TR_REGION)                                         \
+      g_trace[tr_base_ + tr_n_++] = ((unsigned long long)(tag) << 56) | ((unsigned long long)((a) & 0xff) << 48) | \
+                      ((unsigned long long)((b) & 0xff) << 40) | ((unsigned long long)clock64() & 0xffffffffffull); \
+  } while (0)
+#else
+#define TR_DECL(role) do { } while (0)
+#define TR(tag, a, b) do { } while (0)
+#endif
+
+// one non-blocking look at a barrier phase (the blocking form may park the thread for a while)
+__device__ __forceinline__ uint32_t mbar_test(uint32_t saddr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}\n"
+      : "=r"(ok) : "r"(saddr), "r"(parity) : "memory");
+  return ok;
 }
 
 struct PipeBarriers {
@@ -116,7 +189,7 @@ __device__ __forceinline__ float2 fma_f32x2(float2 a, float2 b, float2 c) {
 }
 
 template <int H, bool HB /* h is a bf16 table (else fp32) */, int NG /* producer groups */>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(p_threads(NG), 1)
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(p_maxreg(NG))
 linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, const int *__restrict__ pv,
                     long long M, const MlpParams prm, int L, int apply_sigmoid,
                     const uint8_t *__restrict__ wimg, float *__restrict__ score, int tune, int ring) {
@@ -139,8 +212,9 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
   uint8_t *sW = smem;                                                   // [nhidden][WH_BYTES]
   uint8_t *sRing = sW + (size_t)nhidden * WH_BYTES;                     // [ring][8 KB]
   uint8_t *sA2 = sRing + (size_t)ring * P_STAGE_BYTES;                  // [P_A2_SLOTS][16 KB] (nhidden >= 2)
-  float *sBias = reinterpret_cast<float *>(sA2 + (nhidden >= 2 ? P_A2_SLOTS * A2_SLOT_BYTES : 0));   // [nhidden][H]
-  float *sWlast = sBias + nhidden * H;                                  // [H]
+  uint8_t *sOnes = sA2 + (nhidden >= 2 ? P_A2_SLOTS * A2_SLOT_BYTES : 0);   // [128][16] bf16: A of the bias K-step
+  uint8_t *sBiasB = sOnes + TC_BM * 32;                                 // [nhidden][HH][16] bf16: B of the bias K-step
+  float *sWlast = reinterpret_cast<float *>(sBiasB + (size_t)nhidden * HH * 32);   // [H]
   int2 *sIds = reinterpret_cast<int2 *>(sWlast + H);                    // [2][128] (u, v) of this CTA's rows
   PipeBarriers &bars = *reinterpret_cast<PipeBarriers *>(sIds + 2 * TC_BM);
   cg::cluster_group cluster = cg::this_cluster();
@@ -177,7 +251,27 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
     uint4 *dst = reinterpret_cast<uint4 *>(sW + (size_t)l * WH_BYTES);
     for (int i = tid; i < WH_BYTES / 16; i += P_THREADS) dst[i] = __ldg(src + i);
   }
-  for (int i = tid; i < nhidden * H; i += P_THREADS) sBias[i] = __ldg(prm.b[i / H] + (i % H));
+  // Biases ride in the MMA: one extra K = 16 step per hidden layer with A = [1 1 1 0 ...] for every
+  // row and B[n] = [hi mid lo 0 ...], the bias of output feature n split into three bf16 terms
+  // (hi + mid + lo reproduces the fp32 value to ~2^-24).  The epilogue then never touches shared
+  // memory for a bias, and the accumulator is initialised by this step instead of a zeroing MMA flag.
+  for (int i = tid; i < TC_BM; i += P_THREADS) {
+    const uint32_t one2 = 0x3F803F80u;                               // bf16 (1, 1)
+    *reinterpret_cast<uint4 *>(sOnes + sw32_chunk_off(i, 0)) = make_uint4(one2, 0x00003F80u, 0u, 0u);
+    *reinterpret_cast<uint4 *>(sOnes + sw32_chunk_off(i, 1)) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  for (int i = tid; i < nhidden * HH; i += P_THREADS) {
+    const int l = i / HH, r = i - l * HH;
+    const float b = __ldg(prm.b[l] + cta_rank * HH + r);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+    const float r1 = b - __bfloat162float(hi);
+    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+    const uint32_t w0 = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(mid) << 16);
+    uint8_t *t = sBiasB + (size_t)l * HH * 32;
+    *reinterpret_cast<uint4 *>(t + sw32_chunk_off(r, 0)) = make_uint4(w0, (uint32_t)__bfloat16_as_ushort(lo), 0u, 0u);
+    *reinterpret_cast<uint4 *>(t + sw32_chunk_off(r, 1)) = make_uint4(0u, 0u, 0u, 0u);
+  }
   for (int i = tid; i < H; i += P_THREADS) sWlast[i] = __ldg(prm.W[L - 1] + i);
   const float b_last = __ldg(prm.b[L - 1]);
   fence_async_smem();
@@ -188,73 +282,105 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
 
   const long long npair_tiles = (M + 2 * TC_BM - 1) / (2 * TC_BM);
   const long long nclusters = gridDim.x / 2, cluster_id = blockIdx.x / 2;
+  const int G = (tune & 2) ? 2 : 1;       // tiles per issue group (see the MMA issuer)
 
   if (warp < P_EPI_WARPS) {
     // =============================== EPILOGUE ===============================
-    // Two fp32 adds per FADD2, ReLU fused into the bf16 pack (cvt.rn.relu.bf16x2), biases read with
-    // warp-uniform 128-bit shared loads: a hidden-layer element costs ~1.4 issue slots.
+    // Thread-per-row.  The accumulator already holds W x + b (the bias K-step), so a hidden-layer
+    // element costs one half of a cvt.rn.relu.bf16x2 and an eighth of a 128-bit shared store — no
+    // shared-memory reads at all; the output layer reads its H weights with warp-uniform 128-bit
+    // loads.  The next 32 columns are always in flight (tcgen05.ld) while the current 32 are converted.
+    constexpr int NCH = H / 32;
+    TR_DECL(1);
     uint32_t acph = 0;            // bit s = phase parity of acc_full[s] (kept in a register)
-    uint32_t seq = 0, a2g = 0;    // a2g: activation K-blocks produced so far (slot = a2g % P_A2_SLOTS)
+    uint32_t a2g = 0;             // a2g: activation K-blocks produced so far (slot = a2g % P_A2_SLOTS)
     const int row = warp * 32 + lane;
-    for (long long tile = cluster_id; tile < npair_tiles; tile += nclusters) {
-      const long long p0 = tile * (2 * TC_BM) + (long long)cta_rank * TC_BM;
-      for (int l = 0; l < nhidden; ++l, ++seq) {
-        const uint32_t slot = seq & 1;
+    // Same tile / layer / slot order as the MMA issuer (see there).
+    uint32_t seq = 0;
+    for (long long tile0 = cluster_id; tile0 < npair_tiles; tile0 += G * nclusters) {
+      const int nj = (G == 2 && tile0 + nclusters < npair_tiles) ? 2 : 1;
+      for (int l = 0; l < nhidden; ++l)
+      for (int tj = 0; tj < nj; ++tj) {
+        const long long p0 = (tile0 + tj * nclusters) * (2 * TC_BM) + (long long)cta_rank * TC_BM;
+        const uint32_t slot = G == 2 ? (uint32_t)tj : (seq++ & 1u);
         mbar_wait_cluster(smem_u32(&bars.acc_full[slot]), (acph >> slot) & 1u);
         acph ^= 1u << slot;
         tc_fence_after();
+        if (tid == 0) TR(5, l, tj);
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + slot * H;
-        const float4 *b4 = reinterpret_cast<const float4 *>(sBias + l * H);
+        uint32_t buf[2][32];
+        tmem_ld32_issue(taddr, buf[0]);
         if (l < nhidden - 1) {
-#pragma unroll 1
-          for (int kb = 0; kb < NKB; ++kb, ++a2g) {
-            // K-block kb of the next layer's A operand goes to slot a2g % 3 of the activation ring:
-            // wait until the MMAs that read the slot's previous contents have retired
-            const uint32_t a2s = a2g % P_A2_SLOTS;
-            mbar_wait_cluster(smem_u32(&bars.a2_empty[a2s]), ((a2g / P_A2_SLOTS) & 1u) ^ 1u);
-            uint8_t *dstrow = sA2 + a2s * A2_SLOT_BYTES + row * 128;
+          // The LAST K-block of the tile is converted into registers, not stored: the accumulator slot
+          // is handed back (acc_free) as soon as every column has been read, and only then does the
+          // warp wait for a free slot of the activation ring.  The ring holds fewer K-blocks than a
+          // tile has, and the MMAs that drain it (the next layer of THIS tile) write the very slot
+          // being read here — so they must not be a precondition for finishing the read.
+          uint8_t *dstrow = nullptr;
+          uint32_t a2s = 0;
+          uint4 hold[8];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              const int c0 = kb * 64 + half * 32;
-              float v[32];
-              tmem_ld32(taddr + (uint32_t)c0, v);
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const float4 ba = b4[(c0 + j) >> 2], bc = b4[((c0 + j) >> 2) + 1];
-                const float2 t0 = add_f32x2(make_float2(v[j + 0], v[j + 1]), make_float2(ba.x, ba.y));
-                const float2 t1 = add_f32x2(make_float2(v[j + 2], v[j + 3]), make_float2(ba.z, ba.w));
-                const float2 t2 = add_f32x2(make_float2(v[j + 4], v[j + 5]), make_float2(bc.x, bc.y));
-                const float2 t3 = add_f32x2(make_float2(v[j + 6], v[j + 7]), make_float2(bc.z, bc.w));
-                uint4 o;
-                o.x = cvt_relu_bf16x2(t0.x, t0.y); o.y = cvt_relu_bf16x2(t1.x, t1.y);
-                o.z = cvt_relu_bf16x2(t2.x, t2.y); o.w = cvt_relu_bf16x2(t3.x, t3.y);
-                const int chunk = half * 4 + (j >> 3);
-                *reinterpret_cast<uint4 *>(dstrow + ((chunk ^ (row & 7)) << 4)) = o;
-              }
+          for (int c = 0; c < NCH; ++c) {
+            tmem_ld_wait(buf[c & 1]);
+            if (c + 1 < NCH) tmem_ld32_issue(taddr + (uint32_t)(c + 1) * 32u, buf[(c + 1) & 1]);
+            const bool last_kb = c >= NCH - 2;
+            if (!last_kb && (c & 1) == 0) {
+              // K-block c/2 of the next layer's A operand goes to slot a2g % 3 of the activation ring:
+              // wait until the MMAs that read the slot's previous contents have retired
+              a2s = a2g % P_A2_SLOTS;
+              mbar_wait_cluster(smem_u32(&bars.a2_empty[a2s]), ((a2g / P_A2_SLOTS) & 1u) ^ 1u);
+              dstrow = sA2 + a2s * A2_SLOT_BYTES + row * 128;
             }
-            // the K-block is complete: the tensor pipe starts the next layer on it while the
-            // remaining columns of this tile are still being converted
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.a2_full[a2s]), 0);
+            const uint32_t *v = buf[c & 1];
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 o;
+              o.x = cvt_relu_bf16x2(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
+              o.y = cvt_relu_bf16x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              o.z = cvt_relu_bf16x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+              o.w = cvt_relu_bf16x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+              const int chunk = (c & 1) * 4 + (j >> 3);
+              if (last_kb) hold[chunk] = o;
+              else *reinterpret_cast<uint4 *>(dstrow + ((chunk ^ (row & 7)) << 4)) = o;
+            }
+            if (!last_kb && (c & 1)) {
+              // the K-block is complete: the tensor pipe starts the next layer on it while the
+              // remaining columns of this tile are still being converted
+              fence_async_smem();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.a2_full[a2s]), 0);
+              if (tid == 0) TR(6, c >> 1, tj);
+              ++a2g;
+            }
           }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.acc_free[slot]), 0);
+          if (tid == 0) TR(7, l, tj);
+          a2s = a2g % P_A2_SLOTS;
+          mbar_wait_cluster(smem_u32(&bars.a2_empty[a2s]), ((a2g / P_A2_SLOTS) & 1u) ^ 1u);
+          dstrow = sA2 + a2s * A2_SLOT_BYTES + row * 128;
+#pragma unroll
+          for (int chunk = 0; chunk < 8; ++chunk)
+            *reinterpret_cast<uint4 *>(dstrow + ((chunk ^ (row & 7)) << 4)) = hold[chunk];
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.a2_full[a2s]), 0);
+          if (tid == 0) TR(6, NKB - 1, tj);
+          ++a2g;
         } else {
           const float4 *w4 = reinterpret_cast<const float4 *>(sWlast);
           float2 part = make_float2(0.f, 0.f);
-#pragma unroll 1
-          for (int c0 = 0; c0 < H; c0 += 32) {
-            float v[32];
-            tmem_ld32(taddr + (uint32_t)c0, v);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            tmem_ld_wait(buf[c & 1]);
+            if (c + 1 < NCH) tmem_ld32_issue(taddr + (uint32_t)(c + 1) * 32u, buf[(c + 1) & 1]);
+            const uint32_t *v = buf[c & 1];
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 ba = b4[(c0 + j) >> 2], wa = w4[(c0 + j) >> 2];
-              float2 t0 = add_f32x2(make_float2(v[j + 0], v[j + 1]), make_float2(ba.x, ba.y));
-              float2 t1 = add_f32x2(make_float2(v[j + 2], v[j + 3]), make_float2(ba.z, ba.w));
-              t0.x = fmaxf(t0.x, 0.f); t0.y = fmaxf(t0.y, 0.f);
-              t1.x = fmaxf(t1.x, 0.f); t1.y = fmaxf(t1.y, 0.f);
+              const float4 wa = w4[(c * 32 + j) >> 2];
+              float2 t0 = make_float2(fmaxf(__uint_as_float(v[j + 0]), 0.f), fmaxf(__uint_as_float(v[j + 1]), 0.f));
+              float2 t1 = make_float2(fmaxf(__uint_as_float(v[j + 2]), 0.f), fmaxf(__uint_as_float(v[j + 3]), 0.f));
               part = fma_f32x2(t0, make_float2(wa.x, wa.y), part);
               part = fma_f32x2(t1, make_float2(wa.z, wa.w), part);
             }
@@ -262,6 +388,7 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.acc_free[slot]), 0);
+          if (tid == 0) TR(7, l, tj);
           if (p0 + row < M) {
             const float s = (part.x + part.y) + b_last;
             score[p0 + row] = apply_sigmoid ? sigmoidf_ref(s) : s;
@@ -273,46 +400,81 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
     // =============================== MMA ISSUER (leader CTA, one lane) ===============================
     if (cta_rank == 0 && lane == 0) {   // lanes 1..31 wait at the __syncwarp below (keeps the warp
                                         // converged for the aligned cluster barrier at the end)
-      uint32_t ci = 0, a2g = 0, seq = 0;    // ci: chunks consumed so far (stage = ci % ring); a2g: activation K-blocks
+      TR_DECL(0);
+      // This one thread is the tensor pipe's instruction stream: whatever it executes between two
+      // tcgen05.mma is time the pipe idles once its short queue drains.  So nothing is derived per
+      // iteration — descriptors are a precomputed 64-bit base plus a small constant (the start-address
+      // field counts 16-byte units and never carries out of its 14 bits), ring positions and barrier
+      // phases are carried incrementally (no division by the run-time ring depth).
       uint32_t afph = 0;
-      const uint32_t sW_addr = smem_u32(sW), sRing_addr = smem_u32(sRing), sA2_addr = smem_u32(sA2);
-      for (long long tile = cluster_id; tile < npair_tiles; tile += nclusters) {
-        for (int l = 0; l < nhidden; ++l, ++seq) {
-          const uint32_t slot = seq & 1;
+      const uint64_t dRing = umma_smem_desc_sw64(smem_u32(sRing)), dA2 = umma_smem_desc(smem_u32(sA2));
+      const uint64_t dW = umma_smem_desc(smem_u32(sW));
+      const uint64_t dOnes = umma_smem_desc_sw32(smem_u32(sOnes)), dBias = umma_smem_desc_sw32(smem_u32(sBiasB));
+      const uint32_t full0 = smem_u32(&bars.full[0]), empty0 = smem_u32(&bars.empty[0]);
+      const uint32_t a2full0 = smem_u32(&bars.a2_full[0]), a2empty0 = smem_u32(&bars.a2_empty[0]);
+      uint32_t stage = 0, stage_ph = 0;        // first-layer ring position / parity of full[stage]
+      uint32_t a2s = 0, a2_ph = 0;             // activation ring position / parity of a2_full[a2s]
+      // Issue order.  G = 1: tile by tile, the layers of a tile alternate between the two accumulator
+      // slots (layer l+1 trails the epilogue of layer l K-block by K-block, the next tile's first
+      // layer overlaps the last epilogue).  G = 2 (tune bit 1): layer by layer over a PAIR of tiles,
+      // tile j in slot j, so every dependent step has a whole GEMM of the other tile to hide behind —
+      // at the price of first-layer bursts twice as long for the gather ring to absorb.
+      uint32_t seq = 0;
+      for (long long tile0 = cluster_id; tile0 < npair_tiles; tile0 += G * nclusters) {
+        const int nj = (G == 2 && tile0 + nclusters < npair_tiles) ? 2 : 1;
+        for (int l = 0; l < nhidden; ++l)
+        for (int tj = 0; tj < nj; ++tj) {
+          const uint32_t slot = G == 2 ? (uint32_t)tj : (seq++ & 1u);
           mbar_wait_cluster(smem_u32(&bars.acc_free[slot]), ((afph >> slot) & 1u) ^ 1u);   // first use passes
           afph ^= 1u << slot;
           tc_fence_after();
+          TR(1, l, tj);
           const uint32_t d = tmem_base + slot * H;
+          // bias K-step: initialises the accumulator with b[l] in every row
+          umma_bf16_ss_2cta_p(d, dOnes, dBias + (uint64_t)(l * ((HH * 32) >> 4)), IDESC, 0u);
+          const uint64_t dWl = dW + (uint64_t)(l * (WH_BYTES >> 4));
+          // The barrier of the NEXT stage / K-block is looked at right after the first MMA of the current
+          // one has been issued, so its round trip to shared memory runs under that MMA instead of
+          // between two of them.
           if (l == 0) {
-            for (int c = 0; c < NCHUNK; ++c, ++ci) {
-              const uint32_t stage = ci % (uint32_t)ring;
-              mbar_wait_cluster(smem_u32(&bars.full[stage]), (ci / (uint32_t)ring) & 1u);
+            uint32_t ready = 0;
+#pragma unroll
+            for (int c = 0; c < NCHUNK; ++c) {
+              if (!ready) mbar_wait_cluster(full0 + stage * 8u, stage_ph);
               tc_fence_after();
+              TR(2, c, tj);
+              const uint64_t ad = dRing + (uint64_t)(stage * (P_STAGE_BYTES >> 4));
+              const uint32_t cur = stage;
+              if (++stage == (uint32_t)ring) { stage = 0; stage_ph ^= 1u; }
 #pragma unroll
               for (int k16 = 0; k16 < P_CHUNK_K / 16; ++k16) {
                 const int k = c * P_CHUNK_K + k16 * 16;
-                const uint64_t ad = umma_smem_desc_sw64(sRing_addr + stage * P_STAGE_BYTES + k16 * 32);
-                const uint64_t bd = umma_smem_desc(sW_addr + (k >> 6) * (HH * 128) + ((k & 63) >> 4) * 32);
-                umma_bf16_ss_2cta_p(d, ad, bd, IDESC, (c | k16) ? 1u : 0u);
+                umma_bf16_ss_2cta_p(d, ad + (uint64_t)(k16 * 2),
+                                    dWl + (uint64_t)(((k >> 6) * (HH * 128) + ((k & 63) >> 4) * 32) >> 4), IDESC, 1u);
+                if (k16 == 0) ready = (c + 1 < NCHUNK) ? mbar_test(full0 + stage * 8u, stage_ph) : 0u;
               }
-              umma_commit_mc(smem_u32(&bars.empty[stage]));
+              umma_commit_mc(empty0 + cur * 8u);
             }
           } else {
-#pragma unroll 1
-            for (int kb = 0; kb < NKB; ++kb, ++a2g) {
-              const uint32_t a2s = a2g % P_A2_SLOTS;
-              mbar_wait_cluster(smem_u32(&bars.a2_full[a2s]), (a2g / P_A2_SLOTS) & 1u);   // K-block kb is in place
+            uint32_t ready = 0;
+#pragma unroll
+            for (int kb = 0; kb < NKB; ++kb) {
+              if (!ready) mbar_wait_cluster(a2full0 + a2s * 8u, a2_ph);   // K-block kb is in place
               tc_fence_after();
+              TR(3, kb, tj);
+              const uint64_t ad = dA2 + (uint64_t)(a2s * (A2_SLOT_BYTES >> 4));
+              const uint32_t cur = a2s;
+              if (++a2s == P_A2_SLOTS) { a2s = 0; a2_ph ^= 1u; }
 #pragma unroll
               for (int k16 = 0; k16 < 4; ++k16) {
-                const uint64_t ad = umma_smem_desc(sA2_addr + a2s * A2_SLOT_BYTES + k16 * 32);
-                const uint64_t bd = umma_smem_desc(sW_addr + l * WH_BYTES + kb * (HH * 128) + k16 * 32);
-                umma_bf16_ss_2cta_p(d, ad, bd, IDESC, (kb | k16) ? 1u : 0u);
+                umma_bf16_ss_2cta_p(d, ad + (uint64_t)(k16 * 2), dWl + (uint64_t)((kb * (HH * 128) + k16 * 32) >> 4), IDESC, 1u);
+                if (k16 == 2) ready = (kb + 1 < NKB) ? mbar_test(a2full0 + a2s * 8u, a2_ph) : 0u;
               }
-              umma_commit_mc(smem_u32(&bars.a2_empty[a2s]));      // slot reusable once these MMAs retire
+              umma_commit_mc(a2empty0 + cur * 8u);      // slot reusable once these MMAs retire
             }
           }
           umma_commit_mc(smem_u32(&bars.acc_full[slot]));
+          TR(4, l, tj);
         }
       }
     }
@@ -376,7 +538,13 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
     constexpr int LPR = HB ? 1 : 2;                          // LDG.128 per row and operand
     long long cur_tl = -1;
     int idu[4], idv[4];
-    struct Buf { uint4 xu[4][LPR], xv[4][LPR]; uint32_t valid; };
+    TR_DECL(2 + group);
+    // h[v] is loaded ONCE per thread and chunk: the candidate list is grouped by v (runs of thousands
+    // of pairs), so a thread's four rows almost always share it.  A row whose v differs (a run boundary,
+    // or an arbitrary pair list) fetches its own copy when the buffer is consumed.  Besides a quarter of
+    // the L1 wavefronts this frees 12 registers per buffer, which is what lets two buffers live in the
+    // 96 registers a 576-thread CTA can have.
+    struct Buf { uint4 xu[4][LPR], xv[LPR]; int v[4]; uint32_t valid; };
 
     // Move this warp's position in the pair-id pipeline to tile `tl`: release every tile left behind
     // (also tiles this group has no chunk in — H = 64 has 2 chunks per tile for 3 groups), waiting
@@ -405,32 +573,53 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
         }
       }
       const int boff = (c * P_CHUNK_K + l4 * 8) * (HB ? 2 : 4);
+      if (t == 0) TR(8, c, group);
       b.valid = 0;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
+        b.v[q] = idv[q];
         if (idu[q] >= 0) {
           b.valid |= 1u << q;
           const uint4 *pu4 = reinterpret_cast<const uint4 *>(hbase + (size_t)idu[q] * ROW_BYTES + boff);
-          const uint4 *pv4 = reinterpret_cast<const uint4 *>(hbase + (size_t)idv[q] * ROW_BYTES + boff);
 #pragma unroll
-          for (int j = 0; j < LPR; ++j) { b.xu[q][j] = __ldg(pu4 + j); b.xv[q][j] = __ldg(pv4 + j); }
+          for (int j = 0; j < LPR; ++j) b.xu[q][j] = __ldg(pu4 + j);
         }
       }
+      if (b.valid) {                                         // rows are valid from q = 0 up
+        const uint4 *pv4 = reinterpret_cast<const uint4 *>(hbase + (size_t)idv[0] * ROW_BYTES + boff);
+#pragma unroll
+        for (int j = 0; j < LPR; ++j) b.xv[j] = __ldg(pv4 + j);
+      }
     };
+    // ring position of this group's next chunk and the parity its `empty` barrier is waited with,
+    // carried incrementally (the group's chunks are NG apart and NG < ring: at most one wrap a step)
+    uint32_t pstage = (uint32_t)group, pphase = 1u;
     auto consume = [&](Buf &b, long long i) {
-      const uint32_t stage = (uint32_t)(i % ring);
+      const uint32_t stage = pstage;
       uint8_t *dst = sRing + stage * P_STAGE_BYTES;
-      mbar_wait_cluster(smem_u32(&bars.empty[stage]), (uint32_t)(((i / ring) & 1) ^ 1));   // the MMAs that read this stage retired
+      const int boff = ((int)(i % NCHUNK) * P_CHUNK_K + l4 * 8) * (HB ? 2 : 4);
+      mbar_wait_cluster(smem_u32(&bars.empty[stage]), pphase);   // the MMAs that read this stage retired
+      pstage += NG;
+      if (pstage >= (uint32_t)ring) { pstage -= (uint32_t)ring; pphase ^= 1u; }
+      if (t == 0) TR(9, (int)(i % NCHUNK), group);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int r = rg + 32 * q;
         uint4 o = make_uint4(0u, 0u, 0u, 0u);
         if ((b.valid >> q) & 1u) {
+          uint4 xv[LPR];
+#pragma unroll
+          for (int j = 0; j < LPR; ++j) xv[j] = b.xv[j];
+          if (q > 0 && b.v[q] != b.v[0]) {
+            const uint4 *pv4 = reinterpret_cast<const uint4 *>(hbase + (size_t)b.v[q] * ROW_BYTES + boff);
+#pragma unroll
+            for (int j = 0; j < LPR; ++j) xv[j] = __ldg(pv4 + j);
+          }
           if (HB) {
-            o.x = mul_bf16x2(b.xu[q][0].x, b.xv[q][0].x); o.y = mul_bf16x2(b.xu[q][0].y, b.xv[q][0].y);
-            o.z = mul_bf16x2(b.xu[q][0].z, b.xv[q][0].z); o.w = mul_bf16x2(b.xu[q][0].w, b.xv[q][0].w);
+            o.x = mul_bf16x2(b.xu[q][0].x, xv[0].x); o.y = mul_bf16x2(b.xu[q][0].y, xv[0].y);
+            o.z = mul_bf16x2(b.xu[q][0].z, xv[0].z); o.w = mul_bf16x2(b.xu[q][0].w, xv[0].w);
           } else {
-            const uint4 a0 = b.xu[q][0], a1 = b.xu[q][LPR - 1], c0 = b.xv[q][0], c1 = b.xv[q][LPR - 1];
+            const uint4 a0 = b.xu[q][0], a1 = b.xu[q][LPR - 1], c0 = xv[0], c1 = xv[LPR - 1];
             o.x = hadamard_bf16x2(__uint_as_float(a0.x), __uint_as_float(a0.y), __uint_as_float(c0.x), __uint_as_float(c0.y));
             o.y = hadamard_bf16x2(__uint_as_float(a0.z), __uint_as_float(a0.w), __uint_as_float(c0.z), __uint_as_float(c0.w));
             o.z = hadamard_bf16x2(__uint_as_float(a1.x), __uint_as_float(a1.y), __uint_as_float(c1.x), __uint_as_float(c1.y));
@@ -442,6 +631,7 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.full[stage]), 0);
+      if (t == 0) TR(10, (int)(i % NCHUNK), group);
     };
 
     long long i = group;
@@ -475,7 +665,8 @@ static int tc3_launch_g(const void *h, const int *pu, const int *pv, long long M
                         int apply_sigmoid, float *score, uint8_t *img, cudaStream_t stream) {
   const int nhidden = L - 1;
   const size_t fixed = (size_t)nhidden * (H / 2) * H * 2 + (nhidden >= 2 ? (size_t)P_A2_SLOTS * TC_BM * 128 : 0) +
-                       sizeof(float) * ((size_t)nhidden * H + H) + 2 * TC_BM * sizeof(int2) + sizeof(PipeBarriers);
+                       (size_t)TC_BM * 32 + (size_t)nhidden * (H / 2) * 32 +          // bias K-step tiles
+                       sizeof(float) * (size_t)H + 2 * TC_BM * sizeof(int2) + sizeof(PipeBarriers);
   const size_t budget = 227 * 1024;
   if (fixed + (size_t)(NG + 1) * P_STAGE_BYTES > budget) return EPS_ERR_UNSUPPORTED;   // caller falls back to linkpred_tc2 / tc
   int ring = (int)std::min<size_t>((budget - fixed) / P_STAGE_BYTES, (size_t)P_MAX_RING);
@@ -490,15 +681,26 @@ static int tc3_launch_g(const void *h, const int *pu, const int *pv, long long M
   const int tune = tn ? atoi(tn) : 1;
   kern<<<2 * clusters, p_threads(NG), smem, stream>>>(h, pu, pv, M, prm, L, apply_sigmoid, img, score, tune, ring);
   EPS_LAUNCH_CHECK();
+#ifdef EPS_TC3_TRACE
+  if (const char *tf = getenv("EPS_TC3_TRACE_FILE")) {
+    cudaStreamSynchronize(stream);
+    std::vector<unsigned long long> rec(8 * TR_REGION);
+    cudaMemcpyFromSymbol(rec.data(), g_trace, rec.size() * 8);
+    if (FILE *f = fopen(tf, "wb")) { fwrite(rec.data(), 8, rec.size(), f); fclose(f); }
+    std::fill(rec.begin(), rec.end(), 0ull);
+    cudaMemcpyToSymbol(g_trace, rec.data(), rec.size() * 8);
+  }
+#endif
   return EPS_OK;
 }
 
 template <int H, bool HB>
 static int tc3_launch_h(const void *h, const int *pu, const int *pv, long long M, const MlpParams &prm, int L,
                         int apply_sigmoid, float *score, uint8_t *img, cudaStream_t stream) {
-  const char *g = getenv("EPS_TC3_GROUPS");   // producer groups: 3 (default) or 2 (A/B measurements)
-  if (g && g[0] == '2') return tc3_launch_g<H, HB, 2>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, stream);
-  return tc3_launch_g<H, HB, 3>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, stream);
+  // producer groups: 2 (default: 14 warps -> 128 registers, nothing spills) or 3 (18 warps -> 96 registers)
+  const char *g = getenv("EPS_TC3_GROUPS");
+  if (g && g[0] == '3') return tc3_launch_g<H, HB, 3>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, stream);
+  return tc3_launch_g<H, HB, 2>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, stream);
 }
 
 // fp32 embeddings -> bf16 table (round to nearest even), 8 elements per thread

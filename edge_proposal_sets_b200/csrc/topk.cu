@@ -57,43 +57,74 @@ topk_hist_kernel(const float *__restrict__ score, long long M, const TopkState *
   const uint32_t prefix = PASS ? state->prefix : 0;
   const int lane = lane_id();
   const long long stride = (long long)gridDim.x * TK_THREADS;
-  // whole warps iterate together so the match/ballot below is convergent
+  // whole warps iterate together so the match below is convergent; four strided loads are issued
+  // before the first one is consumed
   const long long start = (long long)blockIdx.x * TK_THREADS + threadIdx.x;
-  const long long mround = ((M + 31) / 32) * 32;
-  for (long long i = start; i - lane < mround && (i - lane) < M; i += stride) {
-    const bool in = i < M;
-    uint32_t key = in ? score_key(score[i]) : 0;
-    const bool ok = in && pass_match<PASS>(key, prefix);
-    // lanes that do not take part get unique ids so they match nobody
-    const uint32_t d = ok ? pass_digit<PASS>(key) : (0x10000u | lane);
-    const unsigned peers = __match_any_sync(FULL, d);
-    if (ok && lane == (__ffs(peers) - 1)) atomicAdd(&sh[d], (uint32_t)__popc(peers));
+  for (long long i = start; i - lane < M; i += 4 * stride) {
+    float sc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long long j = i + q * stride;
+      sc[q] = j < M ? __ldg(score + j) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long long j = i + q * stride;
+      if (j - lane >= M) break;                            // warp-uniform
+      const uint32_t key = score_key(sc[q]);
+      const bool ok = j < M && pass_match<PASS>(key, prefix);
+      // lanes that do not take part share ONE dummy id: match.any costs one round per distinct value
+      // in the warp, and in the later passes almost every lane is outside the prefix bucket
+      const uint32_t d = ok ? pass_digit<PASS>(key) : 0x10000u;
+      const unsigned peers = __match_any_sync(FULL, d);
+      if (ok && lane == (__ffs(peers) - 1)) atomicAdd(&sh[d], (uint32_t)__popc(peers));
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2048; i += TK_THREADS)
     if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 
+// one block of 256 threads: thread t owns bins [8t, 8t+8); block scan of the per-thread totals, then
+// the single thread whose range contains the k_rem-th element walks its eight bins
 template <int PASS>
-__global__ void topk_pick_kernel(TopkState *state, const uint32_t *hist, uint32_t k) {
-  if (threadIdx.x != 0) return;
-  const int nb = (PASS == 2) ? 1024 : 2048;
-  const int shift = (PASS == 0) ? 21 : (PASS == 1 ? 10 : 0);
-  uint32_t k_rem = (PASS == 0) ? k : state->k_rem;
-  uint32_t less = (PASS == 0) ? 0 : state->less_total;
-  uint32_t prefix = (PASS == 0) ? 0 : state->prefix;
-  uint32_t cum = 0;
-  int d = 0;
-  for (; d < nb; ++d) {
-    const uint32_t c = hist[d];
-    if (cum + c >= k_rem) break;
-    cum += c;
+__global__ void __launch_bounds__(256) topk_pick_kernel(TopkState *state, const uint32_t *hist, uint32_t k) {
+  constexpr int NB = (PASS == 2) ? 1024 : 2048;
+  constexpr int PER = NB / 256;
+  constexpr int SHIFT = (PASS == 0) ? 21 : (PASS == 1 ? 10 : 0);
+  __shared__ uint32_t wtot[8];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const uint32_t k_rem = (PASS == 0) ? k : state->k_rem;
+  const uint32_t less = (PASS == 0) ? 0 : state->less_total;
+  const uint32_t prefix = (PASS == 0) ? 0 : state->prefix;
+  uint32_t c[PER], mine = 0;
+#pragma unroll
+  for (int q = 0; q < PER; ++q) { c[q] = hist[t * PER + q]; mine += c[q]; }
+  uint32_t inc = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t y = __shfl_up_sync(FULL, inc, d);
+    if (lane >= d) inc += y;
   }
-  if (d == nb) d = nb - 1;  // cannot happen when k <= M
-  state->prefix = prefix | ((uint32_t)d << shift);
-  state->k_rem = k_rem - cum;
-  state->less_total = less + cum;
-  if (PASS == 2) state->need_eq = k_rem - cum;
+  if (lane == 31) wtot[warp] = inc;
+  __syncthreads();
+  uint32_t base = 0;
+  for (int w = 0; w < warp; ++w) base += wtot[w];
+  const uint32_t before = base + inc - mine;       // elements in bins below this thread's range
+  // the k_rem-th element (1-based) lies in the first bin d with cum(<=d) >= k_rem
+  if (before < k_rem && k_rem <= before + mine) {
+    uint32_t cum = before;
+    int q = 0;
+    for (; q < PER - 1; ++q) {
+      if (cum + c[q] >= k_rem) break;
+      cum += c[q];
+    }
+    const uint32_t d = (uint32_t)(t * PER + q);
+    state->prefix = prefix | (d << SHIFT);
+    state->k_rem = k_rem - cum;
+    state->less_total = less + cum;
+    if (PASS == 2) state->need_eq = k_rem - cum;
+  }
 }
 
 __global__ void __launch_bounds__(TK_THREADS)
@@ -435,11 +466,11 @@ extern "C" int eps_topk_f32(const float *score, int64_t M, int64_t k, uint32_t *
   const long long want = (M + TK_THREADS * 8 - 1) / (TK_THREADS * 8);
   const int hgrid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sms * 8));
   topk_hist_kernel<0><<<hgrid, TK_THREADS, 0, stream>>>(score, M, state, hist);
-  topk_pick_kernel<0><<<1, 32, 0, stream>>>(state, hist, (uint32_t)k);
+  topk_pick_kernel<0><<<1, 256, 0, stream>>>(state, hist, (uint32_t)k);
   topk_hist_kernel<1><<<hgrid, TK_THREADS, 0, stream>>>(score, M, state, hist + 2048);
-  topk_pick_kernel<1><<<1, 32, 0, stream>>>(state, hist + 2048, (uint32_t)k);
+  topk_pick_kernel<1><<<1, 256, 0, stream>>>(state, hist + 2048, (uint32_t)k);
   topk_hist_kernel<2><<<hgrid, TK_THREADS, 0, stream>>>(score, M, state, hist + 4096);
-  topk_pick_kernel<2><<<1, 32, 0, stream>>>(state, hist + 4096, (uint32_t)k);
+  topk_pick_kernel<2><<<1, 256, 0, stream>>>(state, hist + 4096, (uint32_t)k);
   EPS_LAUNCH_CHECK();
   topk_count_kernel<<<L.nblk, TK_THREADS, 0, stream>>>(score, M, state, blk_less, blk_eq);
   scan_exclusive(blk_less, blk_eq, (long long)L.nblk, scan_tmp, stream);

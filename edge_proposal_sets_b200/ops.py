@@ -17,6 +17,9 @@ from .graph import SparseAdj
 
 # kernels launched through this module since the counter was last reset (bench.py reports it)
 LAUNCHES = {"n": 0}
+# optional per-kernel CUDA-event timing on the launching stream: set KERNEL_EVENTS to a dict and every
+# wrapped call appends (start, end) events under its kernel name (bench.py reads them after a sync)
+KERNEL_EVENTS = None
 _TOPK_LAUNCHES = 22      # 3 hist + 3 pick + count + scan + write + 4 x (hist, scan, scatter) + finalize
 
 
@@ -36,6 +39,15 @@ def _need_cuda(*ts):
 
 def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _event_pair(name: str):
+    if KERNEL_EVENTS is None:
+        return None
+    pair = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    pair[0].record()
+    KERNEL_EVENTS.setdefault(name, []).append(pair)
+    return pair
 
 
 def _pairs(edges: torch.Tensor):
@@ -59,9 +71,12 @@ def spmm_csr(rowptr: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor
     y = out if out is not None else torch.empty((n_rows, F), dtype=torch.float32, device=x.device)
     ws = _ws(lib.eps_spmm_workspace_bytes(), x.device)
     red = {"sum": EPS_REDUCE_SUM, "add": EPS_REDUCE_SUM, "mean": EPS_REDUCE_MEAN}[reduce]
+    bias = None if bias is None else bias.contiguous().float()
+    ev = _event_pair("spmm_csr")
     check(lib.eps_spmm_csr_f32(_ptr(rowptr), _ptr(col), _ptr(val), _ptr(x), _ptr(y), n_rows, F, red,
-                               _ptr(None if bias is None else bias.contiguous().float()), int(relu),
-                               _ptr(ws), ws.numel(), _stream()), "eps_spmm_csr_f32")
+                               _ptr(bias), int(relu), _ptr(ws), ws.numel(), _stream()), "eps_spmm_csr_f32")
+    if ev is not None:
+        ev[1].record()
     LAUNCHES["n"] += 1
     return y
 

@@ -6,7 +6,7 @@ i=0
 for envs in "$@"; do
   i=$((i+1))
   if [ "$envs" = "-" ]; then envs=""; fi
-  env $envs timeout 400 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_v${i}.json 2>> gpurun_out/${TAG}_bench.err
+  env $envs timeout 180 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_v${i}.json 2>> gpurun_out/${TAG}_bench.err
   python - <<PY
 import json
 try:
