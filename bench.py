@@ -30,6 +30,16 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE JSON line: keep a private handle to it and point fd 1 at stderr, so that
+# nothing a library prints (NCCL's version banner, torchrun notices) can land next to the result
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    _RESULT_OUT.write(json.dumps(line) + "\n")
+    _RESULT_OUT.flush()
+
 
 def parse():
     p = argparse.ArgumentParser()
@@ -89,6 +99,11 @@ def build_host_inputs(args):
                 x=None if s["x"] is None else torch.from_numpy(s["x"]), sd=sd,
                 dataset="collab" if s["edge_weight"] is not None else args.workload, gen_s=time.time() - t0)
     return host
+
+
+def workload_text(workload: str, slabs: int, k: int) -> str:
+    return (f"{workload}-shape filter step: GCN embeddings once, then {slabs} owner slab(s) per GPU enumerated, "
+            f"scored by AA(+CN) and GCN+LinkPredictor, running top-{k} each")
 
 
 def choose_slab(counts_cum: np.ndarray, start_owner: int, target_pairs: int):
@@ -256,8 +271,11 @@ def run_reference(args):
         "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}-shape filter step, owners [{owners[0]},{owners[1]})",
-                   "n": host["n"], "gnn": f"gcn L={cfg['layers']} H={cfg['hidden']}"},
+        # the B200 arm's workload; each reference step is a bounded sample of it (cpu_baseline.sample)
+        "config": {"workload": workload_text(args.workload, args.slabs, 4_000_000 if args.pairs * args.slabs >= 16_000_000 else max(args.pairs * args.slabs // 8, 1)),
+                   "n": host["n"], "nnz": int(host["edge_index"].shape[1]),
+                   "gnn": f"gcn L={cfg['layers']} H={cfg['hidden']} F_in={cfg['hidden'] + host['feat']}",
+                   "sample_owners": [owners[0], owners[1]]},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": procs, "kind": "port",
                          "sample": f"{last['pairs']} candidates of owners [{owners[0]},{owners[1]}) per step; "
                                    f"scipy A@A enumeration + scipy AA x{procs} procs + torch-CPU MLP + torch sort; "
@@ -266,7 +284,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -557,8 +575,7 @@ def run_b200(args):
             "value": total_pairs / (ms_step * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if mlp_arm == "fp32" else "bf16(mlp)/f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}-shape filter step: GCN embeddings once, then {len(slabs)} owner slab(s) per GPU enumerated, "
-                                   f"scored by AA(+CN) and GCN+LinkPredictor, running top-{k} each",
+            "config": {"workload": workload_text(args.workload, len(slabs), k),
                        "n": n, "nnz": int(h_col.numel()), "candidates_per_gpu": M, "slabs_per_gpu": len(slabs),
                        "slab_candidates": slab_sizes, "owners": [slabs[0][0], slabs[-1][1]],
                        "graph_total_candidates": n_total_candidates, "mean_du_plus_dv": mean_du_dv,
@@ -591,7 +608,7 @@ def run_b200(args):
             except Exception as exc:  # the baseline must never take the bench line down
                 line["cpu_baseline"] = {"value": None, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
                                         "sample": f"failed: {exc!r}"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
