@@ -113,3 +113,43 @@ def reference_candidates(A_scipy_csr):
     coo = A2.tocoo()
     sel = coo.data != 0
     return np.stack([coo.row[sel], coo.col[sel]]).astype(np.int64), coo.data[sel]
+
+
+def _install_model_stubs():
+    """Inert stand-ins for the third-party names /root/reference/models.py imports at module level
+    (models.py:9-29), so that the module itself can be imported and its PLAIN-TORCH members
+    (``LinkPredictor``, ``default_model_configs``) executed unmodified.  The stubs carry no
+    arithmetic: anything that would need torch_geometric / torch_sparse raises when touched."""
+    _install_stubs()
+
+    class _Absent:
+        def __init__(self, *a, **k):
+            raise RuntimeError("torch_geometric / torch_sparse are not installed (inert import stub)")
+
+    def mod(name, **attrs):
+        m = sys.modules.get(name)
+        if m is None:
+            m = types.ModuleType(name)
+            sys.modules[name] = m
+        for k, v in attrs.items():
+            if not hasattr(m, k):
+                setattr(m, k, v)
+        return m
+
+    tg = mod("torch_geometric")
+    tg.transforms = mod("torch_geometric.transforms")
+    tg.nn = mod("torch_geometric.nn", GCNConv=_Absent, SAGEConv=_Absent, TAGConv=_Absent, JumpingKnowledge=_Absent)
+    tg.nn.conv = mod("torch_geometric.nn.conv", MessagePassing=torch.nn.Module)
+    tg.typing = mod("torch_geometric.typing", OptPairTensor=object, Adj=object, Size=object)
+    mod("torch_sparse", SparseTensor=_Absent, sum=_Absent, matmul=_Absent)
+
+
+def reference_models_module():
+    """The reference's ``models`` module, imported unmodified over the inert stubs above."""
+    _install_model_stubs()
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    import importlib
+    m = importlib.import_module("models")
+    assert os.path.abspath(m.__file__).startswith(os.path.abspath(REFERENCE_ROOT)), m.__file__
+    return m
