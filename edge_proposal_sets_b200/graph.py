@@ -127,6 +127,24 @@ class SparseAdj:
                                          p(col2), p(val2), st), "eps_gcn_norm_fill")
         return rowptr2, col2, val2
 
+    def gcn_norm_transposed_values(self):
+        """Values of (GCN-normalised matrix)^T in its own CSR order, for the SpMM backward
+        (autograd.py).  Unweighted: dinv_i*dinv_j is commutative -> ``None`` (same array)."""
+        if self.val is None:
+            return None
+        if "gcn_t" not in self._cache:
+            from .autograd import transposed_values
+            rowptr, col, val = self.gcn_norm()
+            self._cache["gcn_t"] = transposed_values(rowptr, col, val, self.n)
+        return self._cache["gcn_t"]
+
+    def inv_degree(self) -> torch.Tensor:
+        """1/row-length (0 for isolated nodes): the scale of SAGEConv's neighbour mean."""
+        if "inv_deg" not in self._cache:
+            d = self.degree().float()
+            self._cache["inv_deg"] = torch.where(d > 0, 1.0 / d, torch.zeros_like(d))
+        return self._cache["inv_deg"]
+
     def aa_ogb_weights(self) -> torch.Tensor:
         """1/log(A.sum(0)), inf -> 0 (/root/reference/adamic_utils.py:15-16)."""
         if "aa_ogb" not in self._cache:

@@ -14,7 +14,14 @@ What is different is where the arithmetic runs: neighbour aggregation is the K1 
 the (u,v) MLP is the fused K2 kernel, CN/AA is the K3 intersection kernel.  The node embeddings
 ``h`` are computed ONCE per (graph, weights) and cached — the reference recomputes the whole GNN
 for every batch of candidates (models.py:505 inside the loop at filter.py:116-118).
-Inference only (``torch.no_grad`` semantics; dropout is the identity in eval mode).
+
+Two modes, selected like the reference does with ``model.train()`` / ``model.eval()``:
+  * eval (scoring path): fused kernels under ``torch.no_grad`` — K1 with bias/ReLU folded in, K2 with
+    the gather folded in, embeddings cached;
+  * train: the same K1 aggregation kernel behind ``autograd.spmm`` (backward = K1 on
+    the transposed matrix), dropout active, dense layers as torch / cuBLAS ops so that
+    ``loss.backward()`` of /root/reference/train_and_eval.py:31-96 works unchanged.
+Checkpoints in the PyG-2.x GCNConv layout (``convs.i.lin.weight [out,in]``) are accepted on load.
 """
 from __future__ import annotations
 
@@ -22,9 +29,10 @@ import math
 from typing import Optional
 
 import torch
+import torch.nn.functional as F
 from torch import nn
 
-from . import ops
+from . import autograd, ops
 from .graph import SparseAdj
 
 GNN_MODELS = ("gcn", "sage")
@@ -49,7 +57,17 @@ class GCNConv(nn.Module):
     def forward(self, x: torch.Tensor, adj: SparseAdj, relu: bool = False) -> torch.Tensor:
         rowptr, col, val = adj.gcn_norm()
         xw = x @ self.weight                       # dense GEMM stays in the library (cuBLAS fp32)
+        if torch.is_grad_enabled() and (xw.requires_grad or self.bias.requires_grad):
+            out = autograd.spmm(xw, rowptr, col, val, "sum", val_t=adj.gcn_norm_transposed_values()) + self.bias
+            return torch.relu(out) if relu else out
         return ops.spmm_csr(rowptr, col, val, xw, "sum", self.bias, relu)
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        # PyG >= 2.0 stores GCNConv's weight as ``lin.weight [out,in]``
+        k2 = prefix + "lin.weight"
+        if k2 in state_dict and prefix + "weight" not in state_dict:
+            state_dict[prefix + "weight"] = state_dict.pop(k2).t().contiguous()
+        return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
 
 class SAGEConv(nn.Module):
@@ -65,9 +83,12 @@ class SAGEConv(nn.Module):
         self.lin_r.reset_parameters()
 
     def forward(self, x: torch.Tensor, adj: SparseAdj, relu: bool = False) -> torch.Tensor:
-        agg = ops.spmm_csr(adj.rowptr, adj.col, None, x, "mean")   # edge values dropped (A.4)
+        if torch.is_grad_enabled() and x.requires_grad:
+            agg = autograd.spmm(x, adj.rowptr, adj.col, None, "mean", inv_deg=adj.inv_degree())
+        else:
+            agg = ops.spmm_csr(adj.rowptr, adj.col, None, x, "mean")   # edge values dropped (A.4)
         out = self.lin_l(agg) + self.lin_r(x)
-        return torch.relu_(out) if relu else out
+        return torch.relu(out) if relu else out
 
 
 class _ConvStack(nn.Module):
@@ -87,6 +108,8 @@ class _ConvStack(nn.Module):
         last = len(self.convs) - 1
         for i, conv in enumerate(self.convs):
             x = conv(x, adj_t, relu=i != last)    # ReLU fused; dropout is identity in eval
+            if i != last and self.training and self.dropout > 0:
+                x = F.dropout(x, p=self.dropout, training=True)       # models.py:184-185 / 437-438
         return x
 
 
@@ -117,6 +140,11 @@ class LinkPredictor(nn.Module):
 
     def forward(self, x_i, x_j):
         """Reference signature (two gathered [B,H] blocks) kept for callers that use it."""
+        if torch.is_grad_enabled() and (self.training or x_i.requires_grad or x_j.requires_grad):
+            x = x_i * x_j                                             # models.py:478-485, autograd ops
+            for lin in self.lins[:-1]:
+                x = F.dropout(F.relu(lin(x)), p=self.dropout, training=self.training)
+            return torch.sigmoid(self.lins[-1](x))
         B = x_i.shape[0]
         h = torch.cat([x_i, x_j], 0).contiguous()
         ar = torch.arange(B, device=h.device, dtype=torch.int32)
@@ -156,10 +184,15 @@ class LinkGNN(nn.Module):
             self._h_key = key
         return self._h
 
-    @torch.no_grad()
     def forward(self, x, edges, adj):
-        h = self.embed(x, adj)
-        return self.linkpred.score_pairs(h, edges).unsqueeze(1)   # [B,1] like the reference
+        if self.training and torch.is_grad_enabled():
+            # train_and_eval.py:60: the whole GNN runs per batch, with autograd (models.py:500-506)
+            h = self.gnn(self._input(x), adj)
+            e = edges.long()
+            return self.linkpred(h[e[0]], h[e[1]])
+        with torch.no_grad():
+            h = self.embed(x, adj)
+            return self.linkpred.score_pairs(h, edges).unsqueeze(1)   # [B,1] like the reference
 
 
 class CommonNeighborsPredictor(nn.Module):

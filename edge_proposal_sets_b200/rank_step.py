@@ -9,8 +9,7 @@ evaluation, on the same kernels.
   Hits@K                         ogb Evaluator: 1.0 if len(neg) < K else
                                  mean(pos > K-th largest neg), strict '>'
 
-Training (train_and_eval.train, the epoch loop of rank.main) is outside the scoring path: a
-parameterised rank model is evaluated from a checkpoint in the reference's state-dict layout.
+Training of a parameterised rank model: ``train_step.train`` (the epoch loop lives in rank.py).
 """
 from __future__ import annotations
 
@@ -62,15 +61,18 @@ def valid_proposal(sorted_edges: torch.Tensor, valid_pos: torch.Tensor) -> torch
     return out
 
 
-def augmented_graphs(dataset: str, edge_index, edge_weight, extra_edges, split_edge, num_nodes, device):
+def augmented_graphs(dataset: str, edge_index, edge_weight, extra_edges, split_edge, num_nodes, device,
+                     eval_extra=None):
     """(adj_t, full_adj_t) of rank.py:299-314: full adds both directions of the validation edges
-    for collab / email / reddit."""
+    for collab / email / reddit.  ``eval_extra``: the proposal prefix that still enters
+    ``full_adj_t`` when ``--only_supervision`` keeps it out of ``adj_t`` (rank.py:299-312)."""
     ei, ew = edge_index.to(device), edge_weight.to(device)
     adj = add_edges(dataset, ei, ew, extra_edges.to(device), num_nodes)
-    if dataset in ("collab", "email", "reddit"):
+    if dataset.split("-shape")[0] in ("collab", "email", "reddit"):
         v = split_edge["valid"]["edge"].t().to(device)
         vboth = torch.unique(torch.cat([v, v.flip(0)], 1), dim=1)          # to_undirected
-        full = add_edges(dataset, ei, ew, torch.cat([extra_edges.to(device), vboth], 1), num_nodes)
+        fx = (extra_edges if eval_extra is None else eval_extra).to(device)
+        full = add_edges(dataset, ei, ew, torch.cat([fx, vboth], 1), num_nodes)
     else:
         full = adj
     return adj, full
@@ -104,3 +106,42 @@ def evaluate(model_name: str, model, x, adj: SparseAdj, full_adj: SparseAdj, spl
         out[f"Hits@{K}"] = (hits_at_k(pos_train, neg_valid, K), hits_at_k(pos_valid, neg_valid, K),
                             hits_at_k(pos_test, neg_test, K))
     return out
+
+
+class RunLog:
+    """Per-run history of (train, valid, test) Hits for one K, with the summaries the reference
+    prints (/root/reference/logger.py:4-47): best validation epoch decides the reported test value."""
+
+    def __init__(self, runs: int):
+        self.results = [[] for _ in range(runs)]
+
+    def add_result(self, run: int, result):
+        assert len(result) == 3 and 0 <= run < len(self.results)
+        self.results[run].append(tuple(float(v) for v in result))
+
+    def _best(self, run: int):
+        r = 100 * torch.tensor(self.results[run], dtype=torch.float32)
+        am = int(r[:, 1].argmax())
+        return float(r[:, 0].max()), float(r[:, 1].max()), float(r[am, 0]), float(r[am, 2])
+
+    def curve_point(self, run: int, index_end: int):
+        """[index_end, valid, test] at the best-validation epoch (rank.py:377-380)."""
+        r = 100 * torch.tensor(self.results[run], dtype=torch.float32)
+        am = int(r[:, 1].argmax())
+        return [index_end, r[am, 1], r[am, 2]]
+
+    def print_statistics(self, run=None):
+        if run is not None:
+            hi_tr, hi_va, fin_tr, fin_te = self._best(run)
+            print(f"Run {run + 1:02d}:")
+            print(f"Highest Train: {hi_tr:.2f}")
+            print(f"Highest Valid: {hi_va:.2f}")
+            print(f"  Final Train: {fin_tr:.2f}")
+            print(f"   Final Test: {fin_te:.2f}")
+            return
+        best = torch.tensor([self._best(i) for i in range(len(self.results)) if self.results[i]])
+        print("All runs:")
+        for j, label in enumerate(["Highest Train", "Highest Valid", "  Final Train", "   Final Test"]):
+            c = best[:, j]
+            std = c.std() if c.numel() > 1 else torch.tensor(float("nan"))
+            print(f"{label}: {c.mean():.2f} ± {std:.2f}")

@@ -9,11 +9,14 @@ What is kept (the consumer of the filter step, SURVEY §8 a1/a12 and "next" row 
     rebuild ``adj_t`` / ``full_adj_t`` with ``add_edges`` (rank.py:299-314) and evaluate Hits@K
     (train_and_eval.py:98-270) on the GPU kernels; results are printed like the reference and the
     curve point ``[index_end, valid, test]`` is saved under ``curves/``.
-What is NOT rebuilt: the training loop (rank.py:317-361, train_and_eval.train) — it needs autograd
-and is outside the scoring path.  Heuristic rank models (simple / adamic / adamic_ogb /
-resource_allocation) have no parameters and are evaluated exactly as the reference does
-(one "epoch"); a parameterised rank model is evaluated from
-``models/{out_name}|{stem}|{index_end}|{run}.pt`` if that checkpoint exists.
+  * the run / epoch loop of rank.py:317-385: ``model.reset_parameters()``, Adam, one
+    ``train_step.train`` epoch (train_and_eval.py:31-96; K1 forward AND backward through
+    ``autograd.spmm``), evaluation every ``--eval_steps``, ``--save_models`` writes
+    ``models/{out_name}|{stem}|{index_end}|{run}.pt`` at every new best validation Hits@K[1] — the
+    checkpoint ``filter.py`` loads (``{dataset}_{model}||0|0.pt`` for the filter model of
+    submit_job.py:15-17).  Heuristic rank models (simple / adamic / adamic_ogb / resource_allocation)
+    have no parameters and are evaluated once, as in the reference.
+Extension: ``--epochs 0`` evaluates an existing checkpoint of that name without training.
 """
 from __future__ import annotations
 
@@ -59,7 +62,7 @@ def parse_args(argv=None):
 
 
 def main(argv=None):
-    from edge_proposal_sets_b200 import _lib, rank_step
+    from edge_proposal_sets_b200 import _lib, rank_step, train_step
     from edge_proposal_sets_b200.models import build_model, default_model_configs
 
     args = parse_args(argv)
@@ -111,35 +114,67 @@ def main(argv=None):
     use_params = sum(p.numel() for p in model.parameters() if p.requires_grad) > 0
     stem = args.sorted_edge_path.split(".")[0]
     for index_end in index_ends:
+        loggers = {f"Hits@{k}": rank_step.RunLog(args.runs) for k in K}
         print("---------------------")
         print(f"Using {index_end} highest scoring edges")
         print("---------------------")
         extra = rank_step.prefix_edges(sorted_test_edges, index_end)
-        adj, full_adj = rank_step.augmented_graphs(name, edge_index, edge_weight, extra, split_edge,
-                                                   data.num_nodes, device)
-        runs = args.runs if use_params else 1
-        for run in range(runs):
-            if use_params:
-                ckpt = os.path.join("models", f"{args.out_name}|{stem}|{index_end}|{run}.pt")
-                if not os.path.exists(ckpt):
-                    raise SystemExit(f"{ckpt} not found: training a parameterised rank model is outside the "
-                                     "scoring path of this build; train with the reference's rank.py "
-                                     "(--save_models) and re-run to evaluate here")
-                model.load_state_dict(torch.load(ckpt, map_location=device))
-            results = rank_step.evaluate(args.model, model, data.x, adj, full_adj, split_edge, name)
+        if args.only_supervision:                                       # rank.py:299-300: graph untouched
+            no_extra = torch.zeros([2, 0], dtype=torch.long)
+            adj, full_adj = rank_step.augmented_graphs(name, edge_index, edge_weight, no_extra, split_edge,
+                                                       data.num_nodes, device, eval_extra=extra)
+        else:
+            adj, full_adj = rank_step.augmented_graphs(name, edge_index, edge_weight, extra, split_edge,
+                                                       data.num_nodes, device)
+        data.adj_t, data.full_adj_t = adj, full_adj
+        if args.only_supervision or args.also_supervision:               # rank.py:304-305
+            split_edge["train"]["edge"] = torch.cat((split_edge["train"]["edge"], extra.t().cpu()))
+        for run in range(args.runs):
             curve_point = None
-            for key, (tr, va, te) in results.items():
+            model.reset_parameters()
+            print(sum(p.numel() for p in model.parameters() if p.requires_grad))
+            optimizer = torch.optim.Adam(model.parameters(), lr=args.lr) if use_params else None
+            ckpt = os.path.join("models", f"{args.out_name}|{stem}|{index_end}|{run}.pt")
+            epochs = args.epochs if use_params else 1
+            if use_params and args.epochs == 0:
+                # evaluation only: score a checkpoint trained elsewhere (reference layout)
+                model.load_state_dict(torch.load(ckpt, map_location=device))
+                epochs = 1
+            highest_eval = 0
+            for epoch in range(1, 1 + epochs):
+                loss = -1
+                if use_params and args.epochs > 0:
+                    loss = train_step.train(model, data, name, split_edge, optimizer, args.batch_size, use_params,
+                                            args.model, device)
+                if epoch % args.eval_steps != 0:
+                    continue
+                model.eval()
+                results = rank_step.evaluate(args.model, model, data.x, adj, full_adj, split_edge, name)
+                for key, result in results.items():
+                    loggers[key].add_result(run, result)
+                if epoch % args.log_steps == 0:
+                    for key, (tr, va, te) in results.items():
+                        if key == f"Hits@{K[1]}" and va >= highest_eval:
+                            highest_eval = va
+                            if args.save_models and use_params and args.epochs > 0:
+                                torch.save(model.state_dict(), ckpt)
+                        print(key)
+                        print(f"Run: {run + 1:02d}, Epoch: {epoch:02d}, Loss: {loss:.4f}, Train: {100 * tr:.2f}%, "
+                              f"Valid: {100 * va:.2f}%, Test: {100 * te:.2f}%")
+                    print("---")
+            for key in loggers:
                 print(key)
-                print(f"Run: {run + 1:02d}, Epoch: 01, Loss: -1.0000, Train: {100 * tr:.2f}%, "
-                      f"Valid: {100 * va:.2f}%, Test: {100 * te:.2f}%")
+                loggers[key].print_statistics(run)
                 if key == f"Hits@{K[1]}":
-                    curve_point = [index_end, torch.tensor(100 * va), torch.tensor(100 * te)]
-            print("---")
+                    curve_point = loggers[key].curve_point(run, index_end)
             time = datetime.now().strftime("%Y-%m-%d-%H:%M:%S")
             filename = f"{args.out_name}|{stem}|{index_end}|{time}.pt"
             print(curve_point)
             print("Saving curve to ", filename)
             torch.save(curve_point, os.path.join("curves", filename))
+        for key in loggers:
+            print(key)
+            loggers[key].print_statistics()
 
 
 if __name__ == "__main__":
