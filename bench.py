@@ -2,10 +2,11 @@
 """bench.py — candidate pairs scored / second on the ogbl-ppa shape (BASELINE.json metric).
 
 One STEP = the whole filter step (/root/reference/filter.py:92-166) for one slab of owner nodes:
-  K6 count pass -> K6+K3 fused: candidates + Adamic-Adar score + exact CN count of every candidate
+  K6+K3 fused, one pass: candidates + Adamic-Adar score + exact CN count of every candidate
   ->  GCN embeddings (3 x [cuBLAS GEMM + K1 SpMM])
   ->  K2 GCN+LinkPredictor score of every candidate
-  ->  K4 top-k proposal list for each of the two filter models  [-> NCCL all-gather merge, N > 1]
+  ->  K4 running top-k (select over running list ++ slab; one sort at the end) for each of the two
+      filter models  [-> NCCL all-gather merge, N > 1]
 `value` = candidates of the slab / device time of the step (every candidate is scored by BOTH
 filter models; per-scorer rates are reported under `detail`).  Nothing is cached between steps.
 
@@ -57,6 +58,8 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--unfused", action="store_true",
                    help="score CN/AA pair by pair with K3 (eps_cn_aa) after K6 instead of the fused K6+K3 kernel")
+    p.add_argument("--twopass", action="store_true",
+                   help="enumerate with the K6 count pass + prefix sum + fill/fused kernels instead of the one-pass kernel")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
     return p.parse_args()
 
@@ -370,6 +373,7 @@ def run_b200(args):
         lo = hi
     assert slabs, "graph too small for this many ranks x slabs x pairs"
     slab_sizes = [int(cum[b - 1] - (cum[a - 1] if a else 0)) for a, b in slabs]
+    bounds_cum = np.cumsum(candidates.owner_bounds(adj).cpu().numpy())      # slab capacities (host ints)
     M = sum(slab_sizes)
     k = 4_000_000 if M >= 16_000_000 else max(M // 8, 1)
     ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -390,26 +394,32 @@ def run_b200(args):
         hemb = model.embed(x, adj)                            # gcn_norm + L x (GEMM + SpMM)
         aa_w = adj.aa_ogb_weights()
         mark()
-        run_aa = run_nn = None
+        run_aa, run_nn = filter_step.RunningTopK(k), filter_step.RunningTopK(k)
         for (a, b) in slabs:
-            cnt = candidates.owner_counts(adj, a, b)          # K6 count pass (sizes the slab)
+            if args.twopass:
+                cnt, cap = candidates.owner_counts(adj, a, b), None   # K6 count pass (sizes the slab)
+            else:
+                # one-pass kernels: padded owner slots sized by per-owner upper bounds (torch ops, once per graph)
+                cnt = None
+                cap = int(bounds_cum[b - 1] - (bounds_cum[a - 1] if a else 0))
+                candidates.owner_bounds(adj)
             mark()
             if adj.val is None and not args.unfused:
                 # K6+K3 fused: candidates + AA score + exact CN count from one walk over the 2-paths
-                edges, aa, cn = candidates.two_hop_scored(adj, aa_w, a, b, cnt, want_count=True)
+                edges, aa, cn = candidates.two_hop_scored(adj, aa_w, a, b, cnt, want_count=True, cap=cap)
             else:
-                edges = candidates.two_hop(adj, a, b, cnt)
+                edges = candidates.two_hop(adj, a, b, cnt, cap=cap)
                 aa, cn = ops.cn_aa(adj, edges, aa_w, use_values=adj.val is not None, grouped_by_v=True, want_count=True)
             mark()
             sc = model.linkpred.score_pairs(hemb, edges)
             mark()
-            kk = min(k, edges.shape[1])
-            top_aa = ops.topk_edges(edges, aa, kk)
-            top_nn = ops.topk_edges(edges, sc, kk)
-            run_aa = filter_step._merge_running(run_aa, top_aa, k)
-            run_nn = filter_step._merge_running(run_nn, top_nn, k)
+            # K4 select over (running list ++ slab), position-ordered, no sort
+            run_aa.update(edges, aa)
+            run_nn.update(edges, sc)
             mark()
             del edges, aa, cn, sc
+        run_aa, run_nn = run_aa.result(dev), run_nn.result(dev)   # one stable sort of the k survivors each
+        mark()
         if world > 1:
             run_aa = parallel.merge_topk(run_aa, k)
             run_nn = parallel.merge_topk(run_nn, k)
@@ -419,7 +429,7 @@ def run_b200(args):
         return run_aa, run_nn, M
 
     def phase_times(marks):
-        """marks: [start, embed_end, (count_end, score_end, mlp_end, topk_end) x slabs, merge_end]"""
+        """marks: [start, embed_end, (count_end, score_end, mlp_end, topk_end) x slabs, final_sort_end, merge_end]"""
         t = dict.fromkeys(phases, 0.0)
         t["embed"] = marks[0].elapsed_time(marks[1])
         prev = marks[1]
@@ -428,7 +438,8 @@ def run_b200(args):
                 cur = marks[2 + 4 * s_ + j]
                 t[ph] += prev.elapsed_time(cur)
                 prev = cur
-        t["merge"] = prev.elapsed_time(marks[-1])
+        t["topk"] += prev.elapsed_time(marks[-2])
+        t["merge"] = marks[-2].elapsed_time(marks[-1])
         return t
 
     out_host = [torch.empty((k, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -580,6 +591,7 @@ def run_b200(args):
                        "slab_candidates": slab_sizes, "owners": [slabs[0][0], slabs[-1][1]],
                        "graph_total_candidates": n_total_candidates, "mean_du_plus_dv": mean_du_dv,
                        "gnn": f"gcn L={L} H={H} F_in={H + host['feat']}", "mlp_arm": mlp_arm, "k": k,
+                       "enumeration": "two-pass (count + fill)" if args.twopass else "one-pass (padded owner slots + compaction)",
                        "l2": "inputs larger than L2 (pairs+embeddings+CSR > 126 MB); no flush needed"
                        if (M * 8 + n * H * 4) > 200e6 else "inputs smaller than L2: effective (cache-resident) bandwidth"},
             "detail": {"phase_ms": phase_ms,

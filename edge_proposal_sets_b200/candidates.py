@@ -33,13 +33,65 @@ def owner_counts(adj: SparseAdj, v_lo: int = 0, v_hi: int | None = None) -> torc
     return counts.long() & 0xFFFFFFFF
 
 
-def two_hop(adj: SparseAdj, v_lo: int = 0, v_hi: int | None = None, counts: torch.Tensor | None = None):
-    """(u, v) candidate list of owners [v_lo, v_hi): int32 [2, N], column-major reference order."""
+def owner_bounds(adj: SparseAdj) -> torch.Tensor:
+    """Upper bound of every owner's candidate count, int64 [n]: a candidate of v is the end point of
+    a 2-path from v (<= #2-paths) and is neither v nor a neighbour of v (<= n - 1 - deg v).  Torch ops
+    only; sizes the outputs of the one-pass kernel and cuts owner ranges into slabs / GPU shards."""
+    if "owner_bounds" not in adj._cache:
+        deg = adj.degree().long()
+        adj._cache["owner_bounds"] = torch.minimum(two_path_work(adj), (adj.n - 1 - deg).clamp_(min=0))
+    return adj._cache["owner_bounds"]
+
+
+def _onepass(adj: SparseAdj, wtable, v_lo: int, v_hi: int, bounds, sigmoid: bool, want_score: bool, want_count: bool,
+             cap: int | None = None):
+    """eps_twohop_onepass: (edges int32 [2,N] view, score | None, count | None, offsets int64 [n_own+1]).
+    ``bounds``: per-owner upper bounds of the candidate counts (default ``owner_bounds``); ``cap``: their
+    sum when the caller already knows it (filter_step.iter_slabs) — saves a host sync."""
+    lib = _lib.load()
+    dev = adj.device
+    n_own = v_hi - v_lo
+    if n_own <= 0:
+        z = torch.zeros(1, dtype=torch.int64, device=dev)
+        return (torch.empty((2, 0), dtype=torch.int32, device=dev),
+                torch.empty(0, dtype=torch.float32, device=dev) if want_score else None,
+                torch.empty(0, dtype=torch.int32, device=dev) if want_count else None, z)
+    if bounds is None:
+        bounds = owner_bounds(adj)[v_lo:v_hi]
+    boff = torch.zeros(n_own + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(bounds, 0, out=boff[1:])
+    cap = int(boff[-1].item()) if cap is None else int(cap)
+    if cap >= 2**31:
+        raise EpsError(f"up to {cap} candidates in one slab; split the owner range (see filter_step.iter_slabs)")
+    buf = torch.empty((2, max(cap, 1)), dtype=torch.int32, device=dev)
+    score = torch.empty(max(cap, 1), dtype=torch.float32, device=dev) if want_score else None
+    count = torch.empty(max(cap, 1), dtype=torch.int32, device=dev) if want_count else None
+    offsets = torch.empty(n_own + 1, dtype=torch.int64, device=dev)
+    wt = None if wtable is None else wtable.contiguous().float()
+    ws = _ws(lib.eps_twohop_onepass_workspace_bytes(cap, n_own), dev)
+    check(lib.eps_twohop_onepass(_ptr(adj.rowptr), _ptr(adj.col), _ptr(wt), adj.n, v_lo, v_hi, _ptr(boff), cap,
+                                 EPS_CN_SIGMOID if sigmoid else 0, _ptr(buf[0]), _ptr(buf[1]), _ptr(score),
+                                 _ptr(count), _ptr(offsets), _ptr(ws), ws.numel(), _stream()), "eps_twohop_onepass")
+    from . import ops as _ops
+    _ops.LAUNCHES["n"] += 3
+    N = int(offsets[-1].item())                 # the one host sync of the slab (sizes the later launches)
+    if N > cap:
+        raise EpsError(f"eps_twohop_onepass: an owner's candidates exceed the caller's bound (N={N}, cap={cap})")
+    return (buf[:, :N], None if score is None else score[:N], None if count is None else count[:N], offsets)
+
+
+def two_hop(adj: SparseAdj, v_lo: int = 0, v_hi: int | None = None, counts: torch.Tensor | None = None,
+            cap: int | None = None):
+    """(u, v) candidate list of owners [v_lo, v_hi): int32 [2, N], column-major reference order.
+    ``counts`` (from ``owner_counts``) selects the two-pass kernels; without it the one-pass kernel
+    runs (no count pass) and the result is a [2, N] view of a buffer sized by the owner_bounds sum
+    (``cap`` = that sum, when the caller already has it on the host)."""
     _need_cuda(adj.col)
     lib = _lib.load()
     v_hi = adj.n if v_hi is None else v_hi
     if counts is None:
-        counts = owner_counts(adj, v_lo, v_hi)
+        # one pass: padded per-owner slots sized by owner_bounds, compacted by the finalize pass
+        return _onepass(adj, None, v_lo, v_hi, None, False, False, False, cap)[0]
     offsets = torch.zeros(counts.numel() + 1, dtype=torch.int64, device=adj.device)
     torch.cumsum(counts, 0, out=offsets[1:])
     N = int(offsets[-1].item())
@@ -58,19 +110,23 @@ def two_hop(adj: SparseAdj, v_lo: int = 0, v_hi: int | None = None, counts: torc
 
 
 def two_hop_scored(adj: SparseAdj, wtable: torch.Tensor | None = None, v_lo: int = 0, v_hi: int | None = None,
-                   counts: torch.Tensor | None = None, sigmoid: bool = False, want_count: bool = False):
+                   counts: torch.Tensor | None = None, sigmoid: bool = False, want_count: bool = False,
+                   cap: int | None = None):
     """K6+K3 fused: the candidates of owners [v_lo, v_hi) AND their heuristic scores from one walk
     over the owners' 2-paths (``wtable=None`` -> CN count, else sum of ``wtable[k]`` over the common
     neighbours: AA with 1/log deg, RA with 1/deg).  Returns ``(edges int32 [2,N], score fp32 [N])``
     (+ ``count int32 [N]`` with ``want_count``); scores are bit-identical to ``ops.cn_aa`` on the
-    same pairs.  Unweighted adjacency only — weighted graphs go through two_hop + ops.cn_aa."""
+    same pairs.  Unweighted adjacency only — weighted graphs go through two_hop + ops.cn_aa.
+    Without ``counts`` the one-pass kernel runs: no count pass, outputs are views of buffers sized by
+    the owner_bounds sum of the range."""
     _need_cuda(adj.col, wtable)
     if adj.val is not None:
         raise EpsError("two_hop_scored: weighted adjacency (collab) is scored by two_hop + ops.cn_aa")
     lib = _lib.load()
     v_hi = adj.n if v_hi is None else v_hi
     if counts is None:
-        counts = owner_counts(adj, v_lo, v_hi)
+        edges, score, count, _ = _onepass(adj, wtable, v_lo, v_hi, None, sigmoid, True, want_count, cap)
+        return (edges, score, count) if want_count else (edges, score)
     offsets = torch.zeros(counts.numel() + 1, dtype=torch.int64, device=adj.device)
     torch.cumsum(counts, 0, out=offsets[1:])
     N = int(offsets[-1].item())
@@ -93,7 +149,10 @@ def two_hop_scored(adj: SparseAdj, wtable: torch.Tensor | None = None, v_lo: int
 def two_path_work(adj: SparseAdj) -> torch.Tensor:
     """Per-owner work estimate sum_{k in N(v)} deg(k) (the 2-path count), used to cut owner ranges
     into equal-work slabs / GPU shards.  Torch ops only; device-agnostic."""
-    deg = adj.degree().long()
-    contrib = deg[adj.col.long()]
-    out = torch.zeros(adj.n, dtype=torch.int64, device=adj.device)
-    return out.index_add_(0, adj.row(), contrib)
+    if "two_path_work" not in adj._cache:
+        deg = adj.degree().long()
+        cs = torch.zeros(adj.nnz + 1, dtype=torch.int64, device=adj.device)
+        torch.cumsum(deg[adj.col.long()], 0, out=cs[1:])          # segment sums by row: no atomics
+        rp = adj.rowptr.long()
+        adj._cache["two_path_work"] = cs[rp[1:]] - cs[rp[:-1]]
+    return adj._cache["two_path_work"]

@@ -13,6 +13,12 @@
 //   4. a STABLE 4x8-bit LSD radix sort by key alone keeps equal keys in position order.
 // All kernels are HBM streaming passes over `score` (5 reads of 4*M bytes) or over the k
 // survivors; the algorithmic figure is a single 4*M read + 12*k out.
+//
+// Running top-k over owner slabs (eps_topk_select2_f32): the scores are the VIRTUAL concatenation of
+// two segments — A = the running list (position order), B = the new slab — and steps 1-3 are run
+// without step 4: the survivors come out in position order, which is all the next slab needs (the tie
+// rule only looks at positions).  One stable sort at the very end (eps_topk_f32 with k == M) orders
+// the final list, instead of two sorts and two selections per slab.
 #include "eps_common.cuh"
 
 namespace eps {
@@ -26,6 +32,16 @@ struct TopkState {
   uint32_t k_rem;       // rank still to resolve inside the current bucket (1-based)
   uint32_t less_total;  // #{key < prefix-bucket}
   uint32_t need_eq;     // r, written after the last pass
+};
+
+// scores = segment A (na elements) followed by segment B; position i of the concatenation
+struct ScoreSrc {
+  const float *a;
+  long long na;
+  const float *b;
+  __device__ __forceinline__ float at(long long i) const {
+    return i < na ? __ldg(a + i) : __ldg(b + (i - na));
+  }
 };
 
 __device__ __forceinline__ uint32_t score_key(float s) {
@@ -49,7 +65,7 @@ __device__ __forceinline__ uint32_t pass_digit(uint32_t key) {
 
 template <int PASS>
 __global__ void __launch_bounds__(TK_THREADS)
-topk_hist_kernel(const float *__restrict__ score, long long M, const TopkState *state,
+topk_hist_kernel(const ScoreSrc score, long long M, const TopkState *state,
                  uint32_t *__restrict__ hist /*[2048]*/) {
   __shared__ uint32_t sh[2048];
   for (int i = threadIdx.x; i < 2048; i += TK_THREADS) sh[i] = 0;
@@ -65,7 +81,7 @@ topk_hist_kernel(const float *__restrict__ score, long long M, const TopkState *
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const long long j = i + q * stride;
-      sc[q] = j < M ? __ldg(score + j) : 0.f;
+      sc[q] = j < M ? score.at(j) : 0.f;
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -128,7 +144,7 @@ __global__ void __launch_bounds__(256) topk_pick_kernel(TopkState *state, const 
 }
 
 __global__ void __launch_bounds__(TK_THREADS)
-topk_count_kernel(const float *__restrict__ score, long long M, const TopkState *state,
+topk_count_kernel(const ScoreSrc score, long long M, const TopkState *state,
                   uint32_t *__restrict__ blk_less, uint32_t *__restrict__ blk_eq) {
   const uint32_t T = state->prefix;
   const long long base = (long long)blockIdx.x * TK_TILE;
@@ -136,7 +152,7 @@ topk_count_kernel(const float *__restrict__ score, long long M, const TopkState 
   for (int t = threadIdx.x; t < TK_TILE; t += TK_THREADS) {
     const long long i = base + t;
     if (i < M) {
-      const uint32_t key = score_key(score[i]);
+      const uint32_t key = score_key(score.at(i));
       nl += key < T;
       ne += key == T;
     }
@@ -255,7 +271,7 @@ static void scan_exclusive(uint32_t *a, uint32_t *b, long long n, uint32_t *tmp,
 }
 
 __global__ void __launch_bounds__(TK_THREADS)
-topk_write_kernel(const float *__restrict__ score, long long M, const TopkState *state,
+topk_write_kernel(const ScoreSrc score, long long M, const TopkState *state,
                   const uint32_t *__restrict__ blk_less, const uint32_t *__restrict__ blk_eq,
                   uint32_t *__restrict__ out_key, uint32_t *__restrict__ out_idx) {
   const uint32_t T = state->prefix;
@@ -277,7 +293,7 @@ topk_write_kernel(const float *__restrict__ score, long long M, const TopkState 
       const long long i = i0 + q;
       key[q] = 0; cls[q] = 0;
       if (i < M) {
-        key[q] = score_key(score[i]);
+        key[q] = score_key(score.at(i));
         cls[q] = key[q] < T ? 1u : (key[q] == T ? 0x10000u : 0u);
       }
       mine += cls[q];
@@ -380,14 +396,27 @@ sort_scatter_kernel(const uint32_t *__restrict__ key_in, const uint32_t *__restr
   }
 }
 
-__global__ void topk_finalize_kernel(const float *__restrict__ score,
+__global__ void topk_finalize_kernel(const ScoreSrc score,
                                      const uint32_t *__restrict__ idx, uint32_t k,
                                      uint32_t *__restrict__ out_idx, float *__restrict__ out_score) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < k) {
     const uint32_t p = idx[i];
     if (out_idx) out_idx[i] = p;
-    if (out_score) out_score[i] = score[p];
+    if (out_score) out_score[i] = score.at(p);
+  }
+}
+
+// (u, v) of virtual position p: segment A (the running list) first, then segment B (the slab)
+__global__ void gather_pairs2_kernel(const int *__restrict__ ua, const int *__restrict__ va, long long na,
+                                     const int *__restrict__ ub, const int *__restrict__ vb,
+                                     const uint32_t *__restrict__ idx, long long k,
+                                     int *__restrict__ out_u, int *__restrict__ out_v) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < k) {
+    const long long p = idx[i];
+    if (p < na) { out_u[i] = ua[p]; out_v[i] = va[p]; }
+    else        { out_u[i] = ub[p - na]; out_v[i] = vb[p - na]; }
   }
 }
 
@@ -437,20 +466,15 @@ extern "C" size_t eps_topk_workspace_bytes(int64_t M, int64_t k) {
   return eps::topk_layout(M, k).total;
 }
 
-extern "C" int eps_topk_f32(const float *score, int64_t M, int64_t k, uint32_t *out_idx,
-                            float *out_score, void *workspace, size_t workspace_bytes,
-                            void *stream_) {
-  using namespace eps;
-  cudaStream_t stream = (cudaStream_t)stream_;
-  EPS_CHECK_ARG(score != nullptr, "score is NULL");
-  EPS_CHECK_ARG(out_idx || out_score, "no output requested");
-  EPS_CHECK_ARG(M >= 1 && M < 0xffffffffll, "M out of range [1, 2^32-1)");
-  EPS_CHECK_ARG(k >= 1 && k <= M, "k out of range [1, M]");
+namespace eps {
+// steps 1-3 (+ 4 when `sorted`) over the concatenation src = A ++ B of M elements
+static int topk_run(const ScoreSrc src, int64_t M, int64_t k, bool sorted, uint32_t *out_idx, float *out_score,
+                    void *workspace, size_t workspace_bytes, cudaStream_t stream, const char *who) {
   const int sms = sm_count();
-  if (sms <= 0) { set_error("eps_topk_f32: no CUDA device"); return EPS_ERR_CUDA; }
+  if (sms <= 0) { set_error("%s: no CUDA device", who); return EPS_ERR_CUDA; }
   const TopkLayout L = topk_layout(M, k);
   if (!workspace || workspace_bytes < L.total) {
-    set_error("eps_topk_f32: workspace too small (%zu < %zu)", workspace_bytes, L.total);
+    set_error("%s: workspace too small (%zu < %zu)", who, workspace_bytes, L.total);
     return EPS_ERR_WORKSPACE;
   }
   char *ws = (char *)workspace;
@@ -465,19 +489,19 @@ extern "C" int eps_topk_f32(const float *score, int64_t M, int64_t k, uint32_t *
   EPS_CUDA(cudaMemsetAsync(ws + L.state, 0, L.blk_less - L.state, stream));  // state + hist
   const long long want = (M + TK_THREADS * 8 - 1) / (TK_THREADS * 8);
   const int hgrid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sms * 8));
-  topk_hist_kernel<0><<<hgrid, TK_THREADS, 0, stream>>>(score, M, state, hist);
+  topk_hist_kernel<0><<<hgrid, TK_THREADS, 0, stream>>>(src, M, state, hist);
   topk_pick_kernel<0><<<1, 256, 0, stream>>>(state, hist, (uint32_t)k);
-  topk_hist_kernel<1><<<hgrid, TK_THREADS, 0, stream>>>(score, M, state, hist + 2048);
+  topk_hist_kernel<1><<<hgrid, TK_THREADS, 0, stream>>>(src, M, state, hist + 2048);
   topk_pick_kernel<1><<<1, 256, 0, stream>>>(state, hist + 2048, (uint32_t)k);
-  topk_hist_kernel<2><<<hgrid, TK_THREADS, 0, stream>>>(score, M, state, hist + 4096);
+  topk_hist_kernel<2><<<hgrid, TK_THREADS, 0, stream>>>(src, M, state, hist + 4096);
   topk_pick_kernel<2><<<1, 256, 0, stream>>>(state, hist + 4096, (uint32_t)k);
   EPS_LAUNCH_CHECK();
-  topk_count_kernel<<<L.nblk, TK_THREADS, 0, stream>>>(score, M, state, blk_less, blk_eq);
+  topk_count_kernel<<<L.nblk, TK_THREADS, 0, stream>>>(src, M, state, blk_less, blk_eq);
   scan_exclusive(blk_less, blk_eq, (long long)L.nblk, scan_tmp, stream);
-  topk_write_kernel<<<L.nblk, TK_THREADS, 0, stream>>>(score, M, state, blk_less, blk_eq, keyA, idxA);
+  topk_write_kernel<<<L.nblk, TK_THREADS, 0, stream>>>(src, M, state, blk_less, blk_eq, keyA, idxA);
   EPS_LAUNCH_CHECK();
   uint32_t *kin = keyA, *iin = idxA, *kout = keyB, *iout = idxB;
-  for (int pass = 0; pass < 4; ++pass) {
+  for (int pass = 0; sorted && pass < 4; ++pass) {
     const int shift = pass * 8;
     sort_hist_kernel<<<L.nb_sort, TK_THREADS, 0, stream>>>(kin, (uint32_t)k, shift, L.nb_sort, table);
     scan_exclusive(table, nullptr, (long long)256 * L.nb_sort, scan_tmp, stream);
@@ -487,8 +511,46 @@ extern "C" int eps_topk_f32(const float *score, int64_t M, int64_t k, uint32_t *
     std::swap(iin, iout);
   }
   EPS_LAUNCH_CHECK();
-  topk_finalize_kernel<<<(unsigned)((k + 255) / 256), 256, 0, stream>>>(score, iin, (uint32_t)k,
-                                                                       out_idx, out_score);
+  topk_finalize_kernel<<<(unsigned)((k + 255) / 256), 256, 0, stream>>>(src, iin, (uint32_t)k, out_idx, out_score);
+  EPS_LAUNCH_CHECK();
+  return EPS_OK;
+}
+}  // namespace eps
+
+extern "C" int eps_topk_f32(const float *score, int64_t M, int64_t k, uint32_t *out_idx,
+                            float *out_score, void *workspace, size_t workspace_bytes,
+                            void *stream_) {
+  using namespace eps;
+  EPS_CHECK_ARG(score != nullptr, "score is NULL");
+  EPS_CHECK_ARG(out_idx || out_score, "no output requested");
+  EPS_CHECK_ARG(M >= 1 && M < 0xffffffffll, "M out of range [1, 2^32-1)");
+  EPS_CHECK_ARG(k >= 1 && k <= M, "k out of range [1, M]");
+  return topk_run(ScoreSrc{nullptr, 0, score}, M, k, true, out_idx, out_score, workspace, workspace_bytes,
+                  (cudaStream_t)stream_, "eps_topk_f32");
+}
+
+extern "C" int eps_topk_select2_f32(const float *score_a, int64_t Ma, const float *score_b, int64_t Mb,
+                                    int64_t k, uint32_t *out_idx, float *out_score, void *workspace,
+                                    size_t workspace_bytes, void *stream_) {
+  using namespace eps;
+  EPS_CHECK_ARG(Ma >= 0 && Mb >= 0 && (Ma == 0 || score_a) && (Mb == 0 || score_b), "bad segments");
+  EPS_CHECK_ARG(out_idx || out_score, "no output requested");
+  const int64_t M = Ma + Mb;
+  EPS_CHECK_ARG(M >= 1 && M < 0xffffffffll, "Ma + Mb out of range [1, 2^32-1)");
+  EPS_CHECK_ARG(k >= 1 && k <= M, "k out of range [1, Ma + Mb]");
+  return topk_run(ScoreSrc{score_a, Ma, score_b}, M, k, false, out_idx, out_score, workspace, workspace_bytes,
+                  (cudaStream_t)stream_, "eps_topk_select2_f32");
+}
+
+extern "C" int eps_gather_pairs2(const int32_t *ua, const int32_t *va, int64_t Ma, const int32_t *ub,
+                                 const int32_t *vb, const uint32_t *idx, int64_t k, int32_t *out_u,
+                                 int32_t *out_v, void *stream_) {
+  using namespace eps;
+  EPS_CHECK_ARG(idx && out_u && out_v && Ma >= 0 && k >= 0, "null pointer or negative size");
+  EPS_CHECK_ARG(Ma == 0 || (ua && va), "segment A is NULL");
+  if (k == 0) return EPS_OK;
+  gather_pairs2_kernel<<<(unsigned)((k + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
+      ua, va, (long long)Ma, ub, vb, idx, (long long)k, out_u, out_v);
   EPS_LAUNCH_CHECK();
   return EPS_OK;
 }

@@ -22,6 +22,15 @@
 //   5. cleanup  zero the touched bitmap words
 // A tiny element-wise pass then turns the fixed-point sums into fp32 scores (+ sigmoid).
 // Results are bit-identical to eps_cn_aa on the same pairs.
+//
+// Where an owner's output starts:
+//   * two-pass (eps_twohop_scored): from the caller's prefix sum of a separate count pass
+//     (eps_twohop_candidates) — the count pass repeats step 1 for every owner;
+//   * ONE-PASS (eps_twohop_onepass): every owner writes into a PADDED slot whose offset is the prefix sum
+//     of a cheap per-owner upper bound (min(#2-paths, n-1-deg), host-side torch ops), and records its
+//     real count; a single-block scan turns the counts into compact offsets and the finalize pass —
+//     which has to read every accumulator anyway — moves (u, score, count) to the compact position and
+//     regenerates v from the owner id.  No count pass, no inter-CTA dependency.
 #include "eps_common.cuh"
 
 namespace eps {
@@ -132,13 +141,13 @@ struct ScoreVisitor {
   }
 };
 
-template <bool HAS_W, bool WANT_CN>
+template <bool HAS_W, bool WANT_CN, bool ONEPASS>
 __global__ void __launch_bounds__(TS_THREADS)
 twohop_score_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
                     const float *__restrict__ wtable, int n, int v_lo, int v_hi,
                     const long long *__restrict__ offsets, int *__restrict__ pair_u,
                     int *__restrict__ pair_v, unsigned long long *__restrict__ acc, int *__restrict__ cn,
-                    unsigned int *owner_counter) {
+                    unsigned int *owner_counter, unsigned int *__restrict__ counts_out) {
   extern __shared__ uint32_t sm[];
   const int W = (n + 31) >> 5;       // bitmap words
   const int W2 = (W + 31) >> 5;      // blocks of 32 words
@@ -160,7 +169,7 @@ twohop_score_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
     if (v >= v_hi) break;
     const int vs = __ldg(rowptr + v), ve = __ldg(rowptr + v + 1);
     const long long out_base = offsets[v - v_lo];
-    if (offsets[v - v_lo + 1] == out_base) continue;   // no candidates (uniform): bitmap untouched
+    if (offsets[v - v_lo + 1] == out_base) continue;   // no (room for) candidates (uniform): bitmap untouched
     // ---- 1. mark ----
     walk_two_paths(rowptr, col, vs, ve, warp, NW, lane, MarkVisitor{bm, bm2});
     __syncthreads();
@@ -172,7 +181,7 @@ twohop_score_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
     if (tid == 0) atomicAnd(&bm[v >> 5], ~(1u << (v & 31)));
     if (tid == 0) s_carry = 0;
     __syncthreads();
-    // ---- 3. rank + emit; thread t owns block c + t (32 bitmap words) ----
+    // ---- 3a. rank: thread t owns block c + t (32 bitmap words) ----
     for (int c = 0; c < W2; c += TS_THREADS) {
       const int g = c + tid;
       const uint32_t m2 = (g < W2) ? bm2[g] : 0u;
@@ -182,7 +191,9 @@ twohop_score_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
         while (m) {
           const int b = __ffs(m) - 1;
           m &= m - 1;
-          cnt += __popc(bm[g * 32 + b]);
+          const int w = g * 32 + b;
+          pre[w] = (uint16_t)cnt;
+          cnt += __popc(bm[w]);
         }
       }
       uint32_t inc = cnt;
@@ -201,34 +212,53 @@ twohop_score_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
         tot += x;
       }
       const uint32_t carry = s_carry;
-      const uint32_t first = carry + wbase + (inc - cnt);
-      if (g < W2) blk[g] = first;
-      long long o = out_base + first;
-      uint32_t r = 0;
-      uint32_t m = m2;
+      if (g < W2) blk[g] = carry + wbase + (inc - cnt);
+      __syncthreads();
+      if (tid == 0) s_carry = carry + tot;
+    }
+    __syncthreads();
+    if (ONEPASS) {
+      const uint32_t total = s_carry;
+      const bool fits = (long long)total <= offsets[v - v_lo + 1] - out_base;
+      // padded slot: record the real count (a violated bound poisons N instead of overrunning the slot)
+      if (tid == 0) counts_out[v - v_lo] = fits ? total : 0xffffffffu;
+      if (!fits) {
+        for (int g = tid; g < W2; g += TS_THREADS) {
+          uint32_t m = bm2[g];
+          while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            bm[g * 32 + b] = 0;
+          }
+          bm2[g] = 0;
+        }
+        continue;
+      }
+    }
+    // ---- 3b. emit pair_u / pair_v in ascending u ----
+    for (int g = tid; g < W2; g += TS_THREADS) {
+      uint32_t m = bm2[g];
+      long long o = out_base + blk[g];
       while (m) {
         const int b = __ffs(m) - 1;
         m &= m - 1;
         const int w = g * 32 + b;
         uint32_t bits = bm[w];
-        pre[w] = (uint16_t)r;
-        r += __popc(bits);
         while (bits) {
           const int q = __ffs(bits) - 1;
           bits &= bits - 1;
           pair_u[o] = (w << 5) + q;
-          pair_v[o] = v;
+          if (!ONEPASS) pair_v[o] = v;                 // one-pass: v is regenerated by the compaction
           ++o;
         }
       }
-      __syncthreads();
-      if (tid == 0) s_carry = carry + tot;
     }
-    __syncthreads();
     // ---- 4. score: second walk, one integer RED per 2-path that lands on a candidate ----
-    ScoreVisitor<HAS_W, WANT_CN> sv{bm, blk, pre, wtable, HAS_W ? acc + out_base : nullptr,
-                                    WANT_CN ? cn + out_base : nullptr};
-    walk_two_paths(rowptr, col, vs, ve, warp, NW, lane, sv);
+    if (HAS_W || WANT_CN) {
+      ScoreVisitor<HAS_W, WANT_CN> sv{bm, blk, pre, wtable, HAS_W ? acc + out_base : nullptr,
+                                      WANT_CN ? cn + out_base : nullptr};
+      walk_two_paths(rowptr, col, vs, ve, warp, NW, lane, sv);
+    }
     __syncthreads();
     // ---- 5. cleanup ----
     for (int c = 0; c < W2; c += TS_THREADS) {
@@ -254,6 +284,54 @@ twohop_finalize_kernel(const unsigned long long *__restrict__ acc, const int *__
     float sc = acc ? from_fixed(acc[i]) : (float)cn[i];
     if (flags & EPS_CN_SIGMOID) sc = sigmoidf_ref(sc);
     score[i] = sc;
+  }
+}
+
+// single-block exclusive scan of the per-owner counts (uint32 -> int64 offsets[n_own + 1])
+__global__ void __launch_bounds__(1024)
+owner_scan_kernel(const unsigned int *__restrict__ counts, int n_own, long long *__restrict__ offsets) {
+  __shared__ unsigned long long part[1024];
+  const int t = threadIdx.x;
+  const int per = (n_own + 1023) / 1024;
+  const int lo = min(n_own, t * per), hi = min(n_own, lo + per);
+  unsigned long long sum = 0;
+  for (int i = lo; i < hi; ++i) sum += counts[i];
+  part[t] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    unsigned long long y = 0;
+    if (t >= o) y = part[t - o];
+    __syncthreads();
+    part[t] += y;
+    __syncthreads();
+  }
+  unsigned long long run = part[t] - sum;
+  for (int i = lo; i < hi; ++i) { offsets[i] = (long long)run; run += counts[i]; }
+  if (t == 1023) offsets[n_own] = (long long)part[1023];
+}
+
+// padded slot of owner v -> compact position; fixed-point sums -> fp32 scores on the way
+__global__ void __launch_bounds__(256)
+twohop_compact_kernel(const long long *__restrict__ pad_off, const long long *__restrict__ cmp_off,
+                      int v_lo, int n_own, long long cap, const int *__restrict__ pad_u,
+                      const unsigned long long *__restrict__ acc, const int *__restrict__ cn, int flags,
+                      int *__restrict__ pair_u, int *__restrict__ pair_v, float *__restrict__ score,
+                      int *__restrict__ count) {
+  if (cmp_off[n_own] > cap) return;     // a violated bound poisoned N: the caller reports it, nothing is moved
+  for (int o = blockIdx.x; o < n_own; o += gridDim.x) {
+    const long long src = pad_off[o], dst = cmp_off[o];
+    const int cnt = (int)(cmp_off[o + 1] - dst);
+    const int v = v_lo + o;
+    for (int i = threadIdx.x; i < cnt; i += 256) {
+      pair_u[dst + i] = pad_u[src + i];
+      pair_v[dst + i] = v;
+      if (score) {
+        float sc = acc ? from_fixed(acc[src + i]) : (float)cn[src + i];
+        if (flags & EPS_CN_SIGMOID) sc = sigmoidf_ref(sc);
+        score[dst + i] = sc;
+      }
+      if (count) count[dst + i] = cn[src + i];
+    }
   }
 }
 
@@ -298,9 +376,9 @@ extern "C" int eps_twohop_scored(const int32_t *rowptr, const int32_t *col, cons
   }
   if (cn) EPS_CUDA(cudaMemsetAsync(cn, 0, (size_t)N * 4, stream));
   void (*kern)(const int *, const int *, const float *, int, int, int, const long long *, int *, int *,
-               unsigned long long *, int *, unsigned int *);
-  if (wtable) kern = cn ? twohop_score_kernel<true, true> : twohop_score_kernel<true, false>;
-  else kern = twohop_score_kernel<false, true>;
+               unsigned long long *, int *, unsigned int *, unsigned int *);
+  if (wtable) kern = cn ? twohop_score_kernel<true, true, false> : twohop_score_kernel<true, false, false>;
+  else kern = twohop_score_kernel<false, true, false>;
   EPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   EPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TS_THREADS, smem));
@@ -308,11 +386,89 @@ extern "C" int eps_twohop_scored(const int32_t *rowptr, const int32_t *col, cons
   const int grid = (int)std::min<long long>((long long)(v_hi - v_lo), (long long)sms * occ);
   kern<<<grid, TS_THREADS, smem, stream>>>(rowptr, col, wtable, n, v_lo, v_hi,
                                            (const long long *)offsets, pair_u, pair_v, acc, cn,
-                                           (unsigned int *)ws);
+                                           (unsigned int *)ws, nullptr);
   EPS_LAUNCH_CHECK();
   if (score) {
     const int fgrid = (int)std::min<long long>((N + 255) / 256, (long long)sms * 8);
     twohop_finalize_kernel<<<fgrid, 256, 0, stream>>>(acc, cn, (long long)N, flags, score);
+    EPS_LAUNCH_CHECK();
+  }
+  return EPS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one-pass entry: enumerate (+ score) the owner range without a count pass
+// ---------------------------------------------------------------------------------------------
+static inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" size_t eps_twohop_onepass_workspace_bytes(int64_t cap, int32_t n_owners) {
+  const size_t c = (size_t)(cap > 0 ? cap : 0), o = (size_t)(n_owners > 0 ? n_owners : 0);
+  // ticket | per-owner counts | padded u | padded CN counts | padded fixed-point sums
+  return 256 + up256(o * 4) + up256(c * 4) + up256(c * 4) + up256(c * 8);
+}
+
+extern "C" int eps_twohop_onepass(const int32_t *rowptr, const int32_t *col, const float *wtable,
+                                  int32_t n, int32_t v_lo, int32_t v_hi, const int64_t *bound_offsets,
+                                  int64_t cap, int flags, int32_t *pair_u, int32_t *pair_v, float *score,
+                                  int32_t *count, int64_t *offsets_out, void *workspace,
+                                  size_t workspace_bytes, void *stream_) {
+  using namespace eps;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EPS_CHECK_ARG(rowptr && col && bound_offsets && offsets_out, "null graph, bound_offsets or offsets_out pointer");
+  EPS_CHECK_ARG(n > 0 && v_lo >= 0 && v_hi <= n && v_lo < v_hi && cap >= 0, "bad owner range or cap");
+  EPS_CHECK_ARG(cap == 0 || (pair_u && pair_v), "missing pair output pointer");
+  EPS_CHECK_ARG(!(wtable && !score), "wtable given but no score output");
+  const int sms = sm_count();
+  if (sms <= 0) { set_error("eps_twohop_onepass: no CUDA device"); return EPS_ERR_CUDA; }
+  const int n_own = v_hi - v_lo;
+  if (!workspace || workspace_bytes < eps_twohop_onepass_workspace_bytes(cap, n_own)) {
+    set_error("eps_twohop_onepass: workspace too small");
+    return EPS_ERR_WORKSPACE;
+  }
+  const int W = (n + 31) / 32, W2 = (W + 31) / 32;
+  const size_t smem = (size_t)(W + 2 * W2) * 4 + (size_t)W * 2 + 16;
+  if (smem > 200 * 1024) {
+    set_error("eps_twohop_onepass: n=%d needs %zu bytes of shared memory (> 200 KB)", n, smem);
+    return EPS_ERR_UNSUPPORTED;
+  }
+  uint8_t *ws = (uint8_t *)workspace;
+  unsigned int *counts = (unsigned int *)(ws + 256);
+  int *pad_u = (int *)(ws + 256 + up256((size_t)n_own * 4));
+  int *pad_cn = (int *)((uint8_t *)pad_u + up256((size_t)cap * 4));
+  unsigned long long *pad_acc = (unsigned long long *)((uint8_t *)pad_cn + up256((size_t)cap * 4));
+  EPS_CUDA(cudaMemsetAsync(ws, 0, 256 + up256((size_t)n_own * 4), stream));   // ticket + counts
+  const bool want_score = score != nullptr || count != nullptr;
+  unsigned long long *acc = nullptr;
+  int *cn = nullptr;
+  if (wtable) {
+    acc = pad_acc;
+    EPS_CUDA(cudaMemsetAsync(acc, 0, (size_t)cap * 8, stream));
+    if (count) cn = pad_cn;
+  } else if (want_score) {
+    cn = pad_cn;
+  }
+  if (cn) EPS_CUDA(cudaMemsetAsync(cn, 0, (size_t)cap * 4, stream));
+  void (*kern)(const int *, const int *, const float *, int, int, int, const long long *, int *, int *,
+               unsigned long long *, int *, unsigned int *, unsigned int *);
+  if (!want_score) kern = twohop_score_kernel<false, false, true>;
+  else if (wtable) kern = cn ? twohop_score_kernel<true, true, true> : twohop_score_kernel<true, false, true>;
+  else kern = twohop_score_kernel<false, true, true>;
+  EPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  EPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TS_THREADS, smem));
+  if (occ < 1) occ = 1;
+  const int grid = (int)std::min<long long>((long long)n_own, (long long)sms * occ);
+  kern<<<grid, TS_THREADS, smem, stream>>>(rowptr, col, wtable, n, v_lo, v_hi, (const long long *)bound_offsets,
+                                           pad_u, nullptr, acc, cn, (unsigned int *)ws, counts);
+  EPS_LAUNCH_CHECK();
+  owner_scan_kernel<<<1, 1024, 0, stream>>>(counts, n_own, (long long *)offsets_out);
+  EPS_LAUNCH_CHECK();
+  if (cap > 0) {
+    const int cgrid = (int)std::min<long long>((long long)n_own, (long long)sms * 8);
+    twohop_compact_kernel<<<cgrid, 256, 0, stream>>>((const long long *)bound_offsets,
+                                                     (const long long *)offsets_out, v_lo, n_own, (long long)cap,
+                                                     pad_u, acc,
+                                                     cn, flags, pair_u, pair_v, score, count);
     EPS_LAUNCH_CHECK();
   }
   return EPS_OK;

@@ -4,7 +4,7 @@ B200-native restatement of the body of /root/reference/filter.py:92-166:
 
   reference                                         here
   ---------                                         ----
-  A2 = adj@adj on one CPU thread, scipy masking     K6 bitmap enumeration per owner slab
+  A2 = adj@adj on one CPU thread, scipy masking     K6 one-pass bitmap enumeration per owner slab
   for batch in DataLoader(range(N), B):             one K2 / K3 launch per slab
       model(x, edges, adj)   # GNN re-run per batch   embeddings computed once (LinkGNN.embed)
       cat([edges.t(), score]).cpu()                   scores stay on the device
@@ -86,13 +86,14 @@ def ra_graph_from_train_edges(train_edges: torch.Tensor, num_nodes: int) -> Spar
     return SparseAdj(rowptr.int(), (ukey - row * n).int(), None if bool((cnt == 1).all()) else val, n)
 
 
-def iter_slabs(adj: SparseAdj, v_lo: int, v_hi: int, slab_pairs: int) -> Iterator[Tuple[int, int, torch.Tensor]]:
-    """Yield (lo, hi, counts[lo:hi]) owner ranges with at most ``slab_pairs`` candidates each
-    (a single owner with more than that gets a slab of its own)."""
+def iter_slabs(adj: SparseAdj, v_lo: int, v_hi: int, slab_pairs: int) -> Iterator[Tuple[int, int, int]]:
+    """Yield (lo, hi, cap) owner ranges whose candidate count is at most ``cap <= slab_pairs``
+    (a single owner whose bound exceeds that gets a slab of its own).  ``cap`` is the sum of the
+    per-owner upper bounds (candidates.owner_bounds) — it sizes the one-pass kernel's outputs, so no
+    count pass over the graph is needed to plan the slabs."""
     if v_hi <= v_lo:
         return
-    counts = candidates.owner_counts(adj, v_lo, v_hi)
-    cs = torch.cumsum(counts, 0).cpu()
+    cs = torch.cumsum(candidates.owner_bounds(adj)[v_lo:v_hi], 0).cpu()
     lo = 0
     n_own = v_hi - v_lo
     base = 0
@@ -100,21 +101,59 @@ def iter_slabs(adj: SparseAdj, v_lo: int, v_hi: int, slab_pairs: int) -> Iterato
         hi = int(torch.searchsorted(cs, torch.tensor(base + slab_pairs), right=True).item())
         hi = max(hi, lo + 1)
         hi = min(hi, n_own)
-        yield v_lo + lo, v_lo + hi, counts[lo:hi]
-        base = int(cs[hi - 1])
+        end = int(cs[hi - 1])
+        yield v_lo + lo, v_lo + hi, end - base
+        base = end
         lo = hi
 
 
 def _merge_running(running: Optional[torch.Tensor], top: torch.Tensor, k: int) -> torch.Tensor:
+    """Merge two SORTED [*,3] lists (the older one first) into the sorted top-k (used for lists that are
+    already final, e.g. per-GPU results); the slab loop uses ``RunningTopK`` instead."""
     if running is None:
         return top
     cat = torch.cat([running, top], 0)
-    if cat.shape[0] <= k:
-        # both lists are sorted; a stable merge by score == K4 over the concatenation with k = all
-        idx, _ = ops.topk(cat[:, 2].contiguous(), cat.shape[0])
-        return cat[idx]
-    idx, _ = ops.topk(cat[:, 2].contiguous(), k)
+    idx, _ = ops.topk(cat[:, 2].contiguous(), min(k, cat.shape[0]))
     return cat[idx]
+
+
+class RunningTopK:
+    """The proposal set while owner slabs stream by.  State: the current best ``<= k`` candidates as
+    SoA (u, v int32, score fp32) in CANDIDATE ORDER (= the reference's column-major order, which is the
+    tie rule of the final sort).  ``update`` selects the k best of (state ++ slab) with K4's radix
+    select + ordered compaction over the two segments in place — no concatenation, no sort;
+    ``result`` sorts once (stable, score descending) and packs the float32 ``[k,3]`` list.
+    Equal to one global stable sort of all candidates, bit for bit (tests/test_gpu_topk.py)."""
+
+    def __init__(self, k: Optional[int]):
+        self.k = k                      # None: keep every candidate, like the reference
+        self.u = self.v = self.score = None
+        self.seen = 0
+
+    def update(self, edges: torch.Tensor, score: torch.Tensor) -> None:
+        M = score.numel()
+        if M == 0:
+            return
+        self.seen += M
+        pu, pv = ops._pairs(edges)
+        score = score.contiguous().float()
+        have = 0 if self.score is None else self.score.numel()
+        kk = have + M if self.k is None else min(self.k, have + M)
+        if kk == have + M:                                   # everything survives: plain append
+            if self.score is None:
+                self.u, self.v, self.score = pu.clone(), pv.clone(), score.clone()
+            else:
+                self.u, self.v = torch.cat([self.u, pu]), torch.cat([self.v, pv])
+                self.score = torch.cat([self.score, score])
+            return
+        idx, sc = ops.topk_select2(self.score, score, kk)
+        self.u, self.v = ops.gather_pairs2(None if self.score is None else (self.u, self.v), (pu, pv), idx)
+        self.score = sc
+
+    def result(self, device=None) -> torch.Tensor:
+        if self.score is None or self.score.numel() == 0:
+            return torch.empty((0, 3), dtype=torch.float32, device=device)
+        return ops.topk_edges(torch.stack([self.u, self.v]), self.score, self.score.numel())
 
 
 @torch.no_grad()
@@ -128,28 +167,22 @@ def filter_topk(model_name: str, model, x, adj: SparseAdj, k: Optional[int] = No
     if world > 1:
         bounds = parallel.partition_by_work(candidates.two_path_work(adj), world)
         v_lo, v_hi = bounds[rank], bounds[rank + 1]
-    running = None
-    n_scored = 0
+    running = RunningTopK(k)
     fused = heuristic_table(model_name, adj, ra_adj) if model_name not in GNN_MODELS else None
-    for lo, hi, counts in iter_slabs(adj, v_lo, v_hi, slab_pairs):
+    for lo, hi, cap in iter_slabs(adj, v_lo, v_hi, slab_pairs):
         if fused is not None:
             # CN / AA / RA are the values of A@A: one walk over the owners' 2-paths yields the
             # candidates and their scores together (bit-identical to scoring the pairs with K3)
-            edges, score = candidates.two_hop_scored(fused[0], fused[1], lo, hi, counts, sigmoid=fused[2])
+            edges, score = candidates.two_hop_scored(fused[0], fused[1], lo, hi, sigmoid=fused[2], cap=cap)
         else:
-            edges = candidates.two_hop(adj, lo, hi, counts)
-        M = edges.shape[1]
-        if M == 0:
-            continue
-        n_scored += M
-        if fused is None:
-            score = score_edges(model_name, model, x, adj, edges, True, ra_adj)
-        kk = M if k is None else min(k, M)
-        top = ops.topk_edges(edges, score, kk)
-        running = top if running is None else _merge_running(running, top, (running.shape[0] + kk) if k is None else k)
-        del edges, score
-    if running is None:
-        running = torch.empty((0, 3), dtype=torch.float32, device=adj.device)
+            edges = candidates.two_hop(adj, lo, hi, cap=cap)
+            if edges.shape[1]:
+                score = score_edges(model_name, model, x, adj, edges, True, ra_adj)
+        if edges.shape[1]:
+            running.update(edges, score)
+        del edges
+    n_scored = running.seen
+    running = running.result(adj.device)
     if stats is not None:
         stats["candidates_scored"] = n_scored
     if world > 1:

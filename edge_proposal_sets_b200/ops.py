@@ -21,6 +21,7 @@ LAUNCHES = {"n": 0}
 # wrapped call appends (start, end) events under its kernel name (bench.py reads them after a sync)
 KERNEL_EVENTS = None
 _TOPK_LAUNCHES = 22      # 3 hist + 3 pick + count + scan + write + 4 x (hist, scan, scatter) + finalize
+_SELECT_LAUNCHES = 10    # 3 hist + 3 pick + count + scan + write + finalize
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -55,7 +56,8 @@ def _pairs(edges: torch.Tensor):
     if edges.dim() != 2 or edges.shape[0] != 2:
         raise EpsError("edges must have shape [2, M]")
     e = edges if edges.dtype == torch.int32 else edges.to(torch.int32)
-    e = e.contiguous()
+    if e.shape[1] and e.stride(1) != 1:
+        e = e.contiguous()                # rows of a [2,N] view of a wider buffer are already contiguous
     return e[0], e[1]
 
 
@@ -166,3 +168,41 @@ def topk_edges(edges: torch.Tensor, score: torch.Tensor, k: int) -> torch.Tensor
           "eps_pack_edges")
     LAUNCHES["n"] += _TOPK_LAUNCHES + 1
     return out
+
+
+def topk_select2(score_a: Optional[torch.Tensor], score_b: torch.Tensor, k: int):
+    """K4 steps 1-3 over the virtual concatenation ``score_a ++ score_b``: (virtual positions int32 [k]
+    ascending, scores fp32 [k]) of the k best, ties by position.  No sort (see ``RunningTopK``)."""
+    _need_cuda(score_a, score_b)
+    lib = _lib.load()
+    Ma = 0 if score_a is None else score_a.numel()
+    Mb = score_b.numel()
+    assert (score_a is None or (score_a.dtype == torch.float32 and score_a.is_contiguous())) \
+        and score_b.dtype == torch.float32 and score_b.is_contiguous()
+    k = min(int(k), Ma + Mb)
+    idx = torch.empty(k, dtype=torch.int32, device=score_b.device)
+    out = torch.empty(k, dtype=torch.float32, device=score_b.device)
+    if k == 0:
+        return idx, out
+    ws = _ws(lib.eps_topk_workspace_bytes(Ma + Mb, k), score_b.device)
+    check(lib.eps_topk_select2_f32(_ptr(score_a), Ma, _ptr(score_b), Mb, k, _ptr(idx), _ptr(out), _ptr(ws),
+                                   ws.numel(), _stream()), "eps_topk_select2_f32")
+    LAUNCHES["n"] += _SELECT_LAUNCHES
+    return idx, out
+
+
+def gather_pairs2(pairs_a, pairs_b, idx: torch.Tensor):
+    """(u, v) int32 [k] each of the virtual positions ``idx`` over pair segments a ++ b; a segment is
+    a (u, v) tuple of int32 vectors or ``None``."""
+    lib = _lib.load()
+    k = idx.numel()
+    dev = idx.device
+    ou = torch.empty(k, dtype=torch.int32, device=dev)
+    ov = torch.empty(k, dtype=torch.int32, device=dev)
+    ua, va = (None, None) if pairs_a is None else pairs_a
+    ub, vb = (None, None) if pairs_b is None else pairs_b
+    Ma = 0 if ua is None else ua.numel()
+    check(lib.eps_gather_pairs2(_ptr(ua), _ptr(va), Ma, _ptr(ub), _ptr(vb), _ptr(idx), k, _ptr(ou), _ptr(ov),
+                                _stream()), "eps_gather_pairs2")
+    LAUNCHES["n"] += 1 if k else 0
+    return ou, ov

@@ -153,6 +153,26 @@ int eps_pack_edges(const int32_t *pair_u, const int32_t *pair_v, const uint32_t 
                    const float *score, int64_t k, float *out_k3, void *stream);
 
 /* ---------------------------------------------------------------------------
+ * K4 over owner slabs: the running proposal set.
+ * replaces: the same global sort (filter.py:160-161) when the candidates are
+ *           produced slab by slab and never materialised together.
+ *   eps_topk_select2_f32: selection (K4 steps 1-3, no sort) over the virtual
+ *     concatenation score_a[Ma] ++ score_b[Mb] — a = the running list in
+ *     position order, b = the new slab.  out_idx[k] = the positions of the k
+ *     best (ties by position) in ASCENDING POSITION order, out_score[k] their
+ *     scores.  Position order is all the next call needs, so the running list
+ *     is sorted only once, at the end (eps_topk_f32 with k == M).
+ *   eps_gather_pairs2: (u, v) of those positions from the two pair segments.
+ * Workspace: eps_topk_workspace_bytes(Ma + Mb, k).
+ * ------------------------------------------------------------------------- */
+int eps_topk_select2_f32(const float *score_a, int64_t Ma, const float *score_b, int64_t Mb, int64_t k,
+                         uint32_t *out_idx, float *out_score, void *workspace, size_t workspace_bytes,
+                         void *stream);
+int eps_gather_pairs2(const int32_t *ua, const int32_t *va, int64_t Ma, const int32_t *ub,
+                      const int32_t *vb, const uint32_t *idx, int64_t k, int32_t *out_u, int32_t *out_v,
+                      void *stream);
+
+/* ---------------------------------------------------------------------------
  * K6  2-hop candidate enumeration for the owner range [v_lo, v_hi)
  * replaces: A2 = adj_t @ adj_t; remove_diag; A2[adj>0] = 0; nonzero
  *           (/root/reference/filter.py:96-109, CPU, single thread).
@@ -193,6 +213,34 @@ int eps_twohop_scored(const int32_t *rowptr, const int32_t *col, const float *wt
                       int32_t *pair_u, int32_t *pair_v, float *score, int32_t *count,
                       void *workspace, size_t workspace_bytes, void *stream);
 size_t eps_twohop_scored_workspace_bytes(int64_t N);
+
+/* ---------------------------------------------------------------------------
+ * K6 / K6+K3 ONE-PASS  the same enumeration (and, optionally, the same scores)
+ * without the count pass and without a host prefix sum.
+ * replaces: filter.py:96-109 (+ filter.py:113-142 for the heuristic models),
+ *           exactly like eps_twohop_candidates / eps_twohop_scored above.
+ * Every owner writes into a padded slot sized by a cheap upper bound of its
+ * candidate count and records the real count; a scan of the counts and a
+ * finalize pass (fixed point -> fp32, which reads every accumulator anyway)
+ * move the results to their compact positions.  No inter-CTA dependency.
+ *   bound_offsets int64[v_hi - v_lo + 1] (device): exclusive prefix of any
+ *                upper bound of the per-owner candidate counts, e.g.
+ *                min(#2-paths(v), n - 1 - deg(v)); bound_offsets[last] == cap.
+ *                An owner whose real count exceeded its bound would write
+ *                into its neighbour's slot: the bound must hold.
+ *   cap          capacity (in candidates) of pair_u / pair_v / score / count
+ *   offsets_out  int64[v_hi - v_lo + 1] (device): exclusive prefix of the
+ *                real per-owner counts; offsets_out[last] = N <= cap, and the
+ *                first N entries of the outputs are valid.
+ *   wtable / flags / score / count as in eps_twohop_scored; score == NULL and
+ *   count == NULL -> enumeration only (the GNN filter models).
+ * Results are bit-identical to the two-pass entry points.
+ * ------------------------------------------------------------------------- */
+int eps_twohop_onepass(const int32_t *rowptr, const int32_t *col, const float *wtable, int32_t n,
+                       int32_t v_lo, int32_t v_hi, const int64_t *bound_offsets, int64_t cap, int flags,
+                       int32_t *pair_u, int32_t *pair_v, float *score, int32_t *count,
+                       int64_t *offsets_out, void *workspace, size_t workspace_bytes, void *stream);
+size_t eps_twohop_onepass_workspace_bytes(int64_t cap, int32_t n_owners);
 
 /* ---------------------------------------------------------------------------
  * K5  multi-GPU merge of per-GPU proposal lists (no counterpart in the

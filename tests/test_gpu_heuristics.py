@@ -209,6 +209,54 @@ def test_fused_twohop_scored_vs_oracle(shape):
     assert torch.equal(torch.cat([a[0], b[0]], 1), edges) and torch.equal(torch.cat([a[1], b[1]]), aa)
 
 
+@pytest.mark.parametrize("shape", ["tiny", "small", "twitch"])
+def test_onepass_equals_twopass(shape):
+    """eps_twohop_onepass (decoupled look-back, outputs sized by a bound) == count pass + prefix sum +
+    fill / fused kernels, bit for bit: pairs, order, scores, counts, per-owner offsets."""
+    from edge_proposal_sets_b200 import candidates
+    from edge_proposal_sets_b200._lib import EpsError
+    if shape == "twitch":
+        z, ei, g = golden_graph("twitch")
+    else:
+        s, ei, w, g = synth_graph(shape)
+    adj = to_adj(g, DEV)
+    wt = _dev(oh.aa_ogb_weights(g))
+    counts = candidates.owner_counts(adj)
+    N = int(counts.sum())
+    bound = int(candidates.owner_bounds(adj).sum())
+    assert bool((candidates.owner_bounds(adj) >= counts).all()) and bound >= N
+    e2 = candidates.two_hop(adj, counts=counts)
+    e1 = candidates.two_hop(adj)
+    assert e1.shape == (2, N) and torch.equal(e1, e2)
+    f2 = candidates.two_hop_scored(adj, wt, counts=counts, want_count=True)
+    f1 = candidates.two_hop_scored(adj, wt, want_count=True)
+    for a, b in zip(f1, f2):
+        assert torch.equal(a, b)
+    c1 = candidates.two_hop_scored(adj, None)
+    assert torch.equal(c1[0], e2) and torch.equal(c1[1], f2[2].float())
+    sg1 = candidates.two_hop_scored(adj, wt, sigmoid=True)
+    sg2 = candidates.two_hop_scored(adj, wt, counts=counts, sigmoid=True)
+    assert torch.equal(sg1[1], sg2[1])
+    # offsets, a tight capacity, an owner sub-range, and a violated bound
+    e, sc, cn, off = candidates._onepass(adj, wt, 0, adj.n, counts, False, True, True)   # exact bounds
+    assert torch.equal(off[1:], torch.cumsum(counts, 0)) and int(off[0]) == 0
+    assert torch.equal(e, e2) and torch.equal(sc, f2[1]) and torch.equal(cn, f2[2])
+    lo, hi = adj.n // 3, (2 * adj.n) // 3
+    sub = candidates.two_hop_scored(adj, wt, lo, hi, want_count=True)
+    sub2 = candidates.two_hop_scored(adj, wt, lo, hi, counts=counts[lo:hi], want_count=True)
+    for a, b in zip(sub, sub2):
+        assert torch.equal(a, b)
+    short = counts.clone()
+    short[int(torch.argmax(counts))] -= 1                       # one owner's bound one too small
+    with pytest.raises(EpsError):
+        candidates._onepass(adj, wt, 0, adj.n, short, False, True, True)
+    # repeated runs are identical (the look-back is order-independent)
+    for _ in range(3):
+        again = candidates.two_hop_scored(adj, wt, want_count=True)
+        for a, b in zip(again, f2):
+            assert torch.equal(a, b)
+
+
 def test_fused_twohop_scored_tiny_graphs():
     from edge_proposal_sets_b200 import candidates
     for name, (n, e) in tiny_graphs().items():
