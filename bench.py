@@ -404,7 +404,7 @@ def run_b200(args):
                 cap = int(bounds_cum[b - 1] - (bounds_cum[a - 1] if a else 0))
                 candidates.owner_bounds(adj)
             mark()
-            if adj.val is None and not args.unfused:
+            if not args.unfused and (adj.val is None or (cnt is None and candidates.values_symmetric(adj))):
                 # K6+K3 fused: candidates + AA score + exact CN count from one walk over the 2-paths
                 edges, aa, cn = candidates.two_hop_scored(adj, aa_w, a, b, cnt, want_count=True, cap=cap)
             else:
@@ -470,7 +470,7 @@ def run_b200(args):
     # accumulator (zero, RED, read) + 4 B count + 4 B score out
     work = candidates.two_path_work(adj)
     twopaths = int(sum(int(work[a:b].sum().item()) for a, b in slabs))
-    fused_bytes = 8 * twopaths + 28 * M
+    fused_bytes = (8 if adj.val is None else 12) * twopaths + 28 * M    # weighted: + the value next to u
     mlp_flops = M * (2 * H * H * (L - 1) + 3 * H)
     mlp_bytes = M * (2 * H * 4 + 12)
     nnz_hat = int(h_col.numel()) + n                          # GCN adds the self loops
@@ -560,7 +560,7 @@ def run_b200(args):
                 e["note"] = note
             return e
 
-        fused = adj.val is None and not args.unfused
+        fused = not args.unfused and (adj.val is None or (not args.twopass and candidates.values_symmetric(adj)))
         roofs = {
             "mlp": roof_entry("linkpred_fp32_kernel (K2 fp32 arm, FFMA-bound)", "hbm", mlp_bytes, phase_ms["mlp"], S, "mlp_fp32")
             if mlp_arm == "fp32" else

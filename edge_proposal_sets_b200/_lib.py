@@ -42,7 +42,7 @@ SIGNATURES = {
     "eps_twohop_workspace_bytes": (_sz, []),
     "eps_twohop_scored": (_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "eps_twohop_scored_workspace_bytes": (_sz, [_i64]),
-    "eps_twohop_onepass": (_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "eps_twohop_onepass": (_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "eps_twohop_onepass_workspace_bytes": (_sz, [_i64, _i32]),
     "eps_comm_unique_id": (_int, [_vp]),
     "eps_comm_init": (_int, [_vp, _int, _int, C.POINTER(_vp)]),

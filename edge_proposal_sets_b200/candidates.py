@@ -43,8 +43,19 @@ def owner_bounds(adj: SparseAdj) -> torch.Tensor:
     return adj._cache["owner_bounds"]
 
 
+def values_symmetric(adj: SparseAdj) -> bool:
+    """True when A[u,k] == A[k,u] bit for bit (always, for ``add_edges`` graphs with integer-valued
+    weights: both directions receive the same exact sum).  Checked once per graph."""
+    if adj.val is None:
+        return True
+    if "val_sym" not in adj._cache:
+        from .autograd import transposed_values
+        adj._cache["val_sym"] = bool(torch.equal(transposed_values(adj.rowptr, adj.col, adj.val, adj.n), adj.val))
+    return adj._cache["val_sym"]
+
+
 def _onepass(adj: SparseAdj, wtable, v_lo: int, v_hi: int, bounds, sigmoid: bool, want_score: bool, want_count: bool,
-             cap: int | None = None):
+             cap: int | None = None, val: torch.Tensor | None = None):
     """eps_twohop_onepass: (edges int32 [2,N] view, score | None, count | None, offsets int64 [n_own+1]).
     ``bounds``: per-owner upper bounds of the candidate counts (default ``owner_bounds``); ``cap``: their
     sum when the caller already knows it (filter_step.iter_slabs) — saves a host sync."""
@@ -69,7 +80,7 @@ def _onepass(adj: SparseAdj, wtable, v_lo: int, v_hi: int, bounds, sigmoid: bool
     offsets = torch.empty(n_own + 1, dtype=torch.int64, device=dev)
     wt = None if wtable is None else wtable.contiguous().float()
     ws = _ws(lib.eps_twohop_onepass_workspace_bytes(cap, n_own), dev)
-    check(lib.eps_twohop_onepass(_ptr(adj.rowptr), _ptr(adj.col), _ptr(wt), adj.n, v_lo, v_hi, _ptr(boff), cap,
+    check(lib.eps_twohop_onepass(_ptr(adj.rowptr), _ptr(adj.col), _ptr(val), _ptr(wt), adj.n, v_lo, v_hi, _ptr(boff), cap,
                                  EPS_CN_SIGMOID if sigmoid else 0, _ptr(buf[0]), _ptr(buf[1]), _ptr(score),
                                  _ptr(count), _ptr(offsets), _ptr(ws), ws.numel(), _stream()), "eps_twohop_onepass")
     from . import ops as _ops
@@ -111,21 +122,24 @@ def two_hop(adj: SparseAdj, v_lo: int = 0, v_hi: int | None = None, counts: torc
 
 def two_hop_scored(adj: SparseAdj, wtable: torch.Tensor | None = None, v_lo: int = 0, v_hi: int | None = None,
                    counts: torch.Tensor | None = None, sigmoid: bool = False, want_count: bool = False,
-                   cap: int | None = None):
+                   cap: int | None = None, use_values: bool = True):
     """K6+K3 fused: the candidates of owners [v_lo, v_hi) AND their heuristic scores from one walk
     over the owners' 2-paths (``wtable=None`` -> CN count, else sum of ``wtable[k]`` over the common
     neighbours: AA with 1/log deg, RA with 1/deg).  Returns ``(edges int32 [2,N], score fp32 [N])``
     (+ ``count int32 [N]`` with ``want_count``); scores are bit-identical to ``ops.cn_aa`` on the
-    same pairs.  Unweighted adjacency only — weighted graphs go through two_hop + ops.cn_aa.
+    same pairs.  A weighted adjacency (collab, ``use_values``) contributes A[u,k]*(A[v,k]*wtable[k]) per
+    2-path on the one-pass kernel; ``use_values=False`` ignores the values ('adamic', models.py:544-554).
     Without ``counts`` the one-pass kernel runs: no count pass, outputs are views of buffers sized by
     the owner_bounds sum of the range."""
     _need_cuda(adj.col, wtable)
-    if adj.val is not None:
-        raise EpsError("two_hop_scored: weighted adjacency (collab) is scored by two_hop + ops.cn_aa")
+    val = adj.val if use_values else None
+    if val is not None and (counts is not None or not values_symmetric(adj)):
+        raise EpsError("two_hop_scored: a weighted adjacency takes the one-pass kernel (no `counts`) and needs "
+                       "bitwise symmetric values; otherwise score with two_hop + ops.cn_aa")
     lib = _lib.load()
     v_hi = adj.n if v_hi is None else v_hi
     if counts is None:
-        edges, score, count, _ = _onepass(adj, wtable, v_lo, v_hi, None, sigmoid, True, want_count, cap)
+        edges, score, count, _ = _onepass(adj, wtable, v_lo, v_hi, None, sigmoid, True, want_count, cap, val)
         return (edges, score, count) if want_count else (edges, score)
     offsets = torch.zeros(counts.numel() + 1, dtype=torch.int64, device=adj.device)
     torch.cumsum(counts, 0, out=offsets[1:])

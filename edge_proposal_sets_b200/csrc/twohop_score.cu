@@ -39,7 +39,8 @@ constexpr int TS_THREADS = 512;
 constexpr int TS_LONG = 96;   // lists at least this long are streamed warp-wide without a search
 
 // Visit every element of the neighbour lists of N(v) (a warp takes 32 lists at a time).
-// f(u, slot) is called once per 2-path v - k - u; `slot` is the lane that holds k's metadata.
+// f.visit(u, p) is called once per 2-path v - k - u (p = index of u in `col`, i.e. inside N(k)) after
+// f.select_slot*(lane that holds k's metadata).
 template <typename F>
 __device__ __forceinline__ void walk_two_paths(const int *__restrict__ rowptr, const int *__restrict__ col,
                                                int vs, int ve, int warp, int nwarps, int lane, F f) {
@@ -50,7 +51,7 @@ __device__ __forceinline__ void walk_two_paths(const int *__restrict__ rowptr, c
       s = __ldg(rowptr + k);
       len = __ldg(rowptr + k + 1) - s;
     }
-    f.load_slot(k);
+    f.load_slot(k, base + lane);
     // ---- long lists: the whole warp streams one list, 4 loads in flight per lane ----
     unsigned longmask = __ballot_sync(FULL, len >= TS_LONG);
     while (longmask) {
@@ -69,7 +70,7 @@ __device__ __forceinline__ void walk_two_paths(const int *__restrict__ rowptr, c
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (u[q] >= 0) f.visit(u[q]);
+          if (u[q] >= 0) f.visit(u[q], sb + off + q * 32 + lane);
       }
     }
     // ---- short lists: one flattened sequence ----
@@ -93,17 +94,17 @@ __device__ __forceinline__ void walk_two_paths(const int *__restrict__ rowptr, c
       const int s_t = __shfl_sync(FULL, s, lo);
       const int pe_t = __shfl_sync(FULL, pex, lo);
       f.select_slot_lane(lo);
-      if (p < total) f.visit(__ldg(col + s_t + (p - pe_t)));
+      if (p < total) f.visit(__ldg(col + s_t + (p - pe_t)), s_t + (p - pe_t));
     }
   }
 }
 
 struct MarkVisitor {
   uint32_t *bm, *bm2;
-  __device__ __forceinline__ void load_slot(int) {}
+  __device__ __forceinline__ void load_slot(int, int) {}
   __device__ __forceinline__ void select_slot(int) {}
   __device__ __forceinline__ void select_slot_lane(int) {}
-  __device__ __forceinline__ void visit(int u) {
+  __device__ __forceinline__ void visit(int u, int) {
     const uint32_t bit = 1u << (u & 31);
     const int w = u >> 5;
     if (!(bm[w] & bit)) {                          // cheap pre-test: most bits are already set
@@ -113,37 +114,51 @@ struct MarkVisitor {
   }
 };
 
-template <bool HAS_W, bool WANT_CN>
+// Weighted adjacency (HAS_VAL, collab): the term of the 2-path v - k - u is a_u * (a_v * w_k) (or a_u * a_v
+// without a weight table) with a_v = A[v,k] (the value next to k in N(v)) and a_u = A[k,u] (next to u in
+// N(k)) — the same fp32 products as eps_cn_aa forms from A[u,k]; the caller guarantees A[k,u] == A[u,k]
+// bit for bit (candidates.py checks it once per graph).
+template <bool HAS_W, bool WANT_CN, bool HAS_VAL>
 struct ScoreVisitor {
   const uint32_t *bm, *blk;
   const uint16_t *pre;
   const float *__restrict__ wtable;
+  const float *__restrict__ val;
   unsigned long long *acc;   // + out_base already applied
   int *cn;
   unsigned long long fx_slot = 0ull, fx = 0ull;
-  __device__ __forceinline__ void load_slot(int k) {
-    if (HAS_W) fx_slot = k >= 0 ? to_fixed(__ldg(wtable + k)) : 0ull;
+  float sv_slot = 0.f, sv = 0.f;
+  __device__ __forceinline__ void load_slot(int k, int pos) {
+    if (HAS_VAL) {
+      const float a_v = k >= 0 ? __ldg(val + pos) : 0.f;
+      sv_slot = (HAS_W && k >= 0) ? __fmul_rn(a_v, __ldg(wtable + k)) : a_v;
+    } else if (HAS_W) {
+      fx_slot = k >= 0 ? to_fixed(__ldg(wtable + k)) : 0ull;
+    }
   }
   __device__ __forceinline__ void select_slot(int b) {           // warp-uniform slot
-    if (HAS_W) fx = __shfl_sync(FULL, fx_slot, b);
+    if (HAS_VAL) sv = __shfl_sync(FULL, sv_slot, b);
+    else if (HAS_W) fx = __shfl_sync(FULL, fx_slot, b);
   }
   __device__ __forceinline__ void select_slot_lane(int lo) {     // per-lane slot
-    if (HAS_W) fx = __shfl_sync(FULL, fx_slot, lo);
+    if (HAS_VAL) sv = __shfl_sync(FULL, sv_slot, lo);
+    else if (HAS_W) fx = __shfl_sync(FULL, fx_slot, lo);
   }
-  __device__ __forceinline__ void visit(int u) {
+  __device__ __forceinline__ void visit(int u, int p) {
     const int w = u >> 5, b = u & 31;
     const uint32_t word = bm[w];
     if ((word >> b) & 1u) {
       const uint32_t idx = blk[w >> 5] + pre[w] + __popc(word & ((1u << b) - 1u));
-      if (HAS_W) atomicAdd(acc + idx, fx);
+      if (HAS_VAL) atomicAdd(acc + idx, to_fixed(__fmul_rn(__ldg(val + p), sv)));
+      else if (HAS_W) atomicAdd(acc + idx, fx);
       if (WANT_CN) atomicAdd(cn + idx, 1);
     }
   }
 };
 
-template <bool HAS_W, bool WANT_CN, bool ONEPASS>
+template <bool HAS_W, bool WANT_CN, bool ONEPASS, bool HAS_VAL = false>
 __global__ void __launch_bounds__(TS_THREADS)
-twohop_score_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
+twohop_score_kernel(const int *__restrict__ rowptr, const int *__restrict__ col, const float *__restrict__ val,
                     const float *__restrict__ wtable, int n, int v_lo, int v_hi,
                     const long long *__restrict__ offsets, int *__restrict__ pair_u,
                     int *__restrict__ pair_v, unsigned long long *__restrict__ acc, int *__restrict__ cn,
@@ -254,9 +269,10 @@ twohop_score_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
       }
     }
     // ---- 4. score: second walk, one integer RED per 2-path that lands on a candidate ----
-    if (HAS_W || WANT_CN) {
-      ScoreVisitor<HAS_W, WANT_CN> sv{bm, blk, pre, wtable, HAS_W ? acc + out_base : nullptr,
-                                      WANT_CN ? cn + out_base : nullptr};
+    if (HAS_W || WANT_CN || HAS_VAL) {
+      ScoreVisitor<HAS_W, WANT_CN, HAS_VAL> sv{bm, blk, pre, wtable, val,
+                                               (HAS_W || HAS_VAL) ? acc + out_base : nullptr,
+                                               WANT_CN ? cn + out_base : nullptr};
       walk_two_paths(rowptr, col, vs, ve, warp, NW, lane, sv);
     }
     __syncthreads();
@@ -375,8 +391,8 @@ extern "C" int eps_twohop_scored(const int32_t *rowptr, const int32_t *col, cons
     cn = (int *)(ws + 256);          // CN scores only: count lives in the workspace
   }
   if (cn) EPS_CUDA(cudaMemsetAsync(cn, 0, (size_t)N * 4, stream));
-  void (*kern)(const int *, const int *, const float *, int, int, int, const long long *, int *, int *,
-               unsigned long long *, int *, unsigned int *, unsigned int *);
+  void (*kern)(const int *, const int *, const float *, const float *, int, int, int, const long long *, int *,
+               int *, unsigned long long *, int *, unsigned int *, unsigned int *);
   if (wtable) kern = cn ? twohop_score_kernel<true, true, false> : twohop_score_kernel<true, false, false>;
   else kern = twohop_score_kernel<false, true, false>;
   EPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -384,7 +400,7 @@ extern "C" int eps_twohop_scored(const int32_t *rowptr, const int32_t *col, cons
   EPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TS_THREADS, smem));
   if (occ < 1) occ = 1;
   const int grid = (int)std::min<long long>((long long)(v_hi - v_lo), (long long)sms * occ);
-  kern<<<grid, TS_THREADS, smem, stream>>>(rowptr, col, wtable, n, v_lo, v_hi,
+  kern<<<grid, TS_THREADS, smem, stream>>>(rowptr, col, nullptr, wtable, n, v_lo, v_hi,
                                            (const long long *)offsets, pair_u, pair_v, acc, cn,
                                            (unsigned int *)ws, nullptr);
   EPS_LAUNCH_CHECK();
@@ -407,8 +423,8 @@ extern "C" size_t eps_twohop_onepass_workspace_bytes(int64_t cap, int32_t n_owne
   return 256 + up256(o * 4) + up256(c * 4) + up256(c * 4) + up256(c * 8);
 }
 
-extern "C" int eps_twohop_onepass(const int32_t *rowptr, const int32_t *col, const float *wtable,
-                                  int32_t n, int32_t v_lo, int32_t v_hi, const int64_t *bound_offsets,
+extern "C" int eps_twohop_onepass(const int32_t *rowptr, const int32_t *col, const float *val,
+                                  const float *wtable, int32_t n, int32_t v_lo, int32_t v_hi, const int64_t *bound_offsets,
                                   int64_t cap, int flags, int32_t *pair_u, int32_t *pair_v, float *score,
                                   int32_t *count, int64_t *offsets_out, void *workspace,
                                   size_t workspace_bytes, void *stream_) {
@@ -418,6 +434,7 @@ extern "C" int eps_twohop_onepass(const int32_t *rowptr, const int32_t *col, con
   EPS_CHECK_ARG(n > 0 && v_lo >= 0 && v_hi <= n && v_lo < v_hi && cap >= 0, "bad owner range or cap");
   EPS_CHECK_ARG(cap == 0 || (pair_u && pair_v), "missing pair output pointer");
   EPS_CHECK_ARG(!(wtable && !score), "wtable given but no score output");
+  EPS_CHECK_ARG(!(val && !score), "edge values given but no score output");
   const int sms = sm_count();
   if (sms <= 0) { set_error("eps_twohop_onepass: no CUDA device"); return EPS_ERR_CUDA; }
   const int n_own = v_hi - v_lo;
@@ -440,7 +457,7 @@ extern "C" int eps_twohop_onepass(const int32_t *rowptr, const int32_t *col, con
   const bool want_score = score != nullptr || count != nullptr;
   unsigned long long *acc = nullptr;
   int *cn = nullptr;
-  if (wtable) {
+  if (wtable || val) {
     acc = pad_acc;
     EPS_CUDA(cudaMemsetAsync(acc, 0, (size_t)cap * 8, stream));
     if (count) cn = pad_cn;
@@ -448,9 +465,11 @@ extern "C" int eps_twohop_onepass(const int32_t *rowptr, const int32_t *col, con
     cn = pad_cn;
   }
   if (cn) EPS_CUDA(cudaMemsetAsync(cn, 0, (size_t)cap * 4, stream));
-  void (*kern)(const int *, const int *, const float *, int, int, int, const long long *, int *, int *,
-               unsigned long long *, int *, unsigned int *, unsigned int *);
+  void (*kern)(const int *, const int *, const float *, const float *, int, int, int, const long long *, int *,
+               int *, unsigned long long *, int *, unsigned int *, unsigned int *);
   if (!want_score) kern = twohop_score_kernel<false, false, true>;
+  else if (val && wtable) kern = cn ? twohop_score_kernel<true, true, true, true> : twohop_score_kernel<true, false, true, true>;
+  else if (val) kern = cn ? twohop_score_kernel<false, true, true, true> : twohop_score_kernel<false, false, true, true>;
   else if (wtable) kern = cn ? twohop_score_kernel<true, true, true> : twohop_score_kernel<true, false, true>;
   else kern = twohop_score_kernel<false, true, true>;
   EPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -458,8 +477,9 @@ extern "C" int eps_twohop_onepass(const int32_t *rowptr, const int32_t *col, con
   EPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TS_THREADS, smem));
   if (occ < 1) occ = 1;
   const int grid = (int)std::min<long long>((long long)n_own, (long long)sms * occ);
-  kern<<<grid, TS_THREADS, smem, stream>>>(rowptr, col, wtable, n, v_lo, v_hi, (const long long *)bound_offsets,
-                                           pad_u, nullptr, acc, cn, (unsigned int *)ws, counts);
+  kern<<<grid, TS_THREADS, smem, stream>>>(rowptr, col, val, wtable, n, v_lo, v_hi,
+                                           (const long long *)bound_offsets, pad_u, nullptr, acc, cn,
+                                           (unsigned int *)ws, counts);
   EPS_LAUNCH_CHECK();
   owner_scan_kernel<<<1, 1024, 0, stream>>>(counts, n_own, (long long *)offsets_out);
   EPS_LAUNCH_CHECK();

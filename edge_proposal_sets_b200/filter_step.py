@@ -54,20 +54,20 @@ def same_structure(a: SparseAdj, b: SparseAdj) -> bool:
 
 
 def heuristic_table(model_name: str, adj: SparseAdj, ra_adj: Optional[SparseAdj] = None):
-    """(graph, weight table, sigmoid) of a heuristic filter model when it can take the fused
-    enumerate+score kernel (K6+K3, candidates.two_hop_scored): unweighted adjacency, and the scoring
-    graph IS the graph whose 2-hop neighbourhood defines the candidates.  ``None`` otherwise
-    (collab's weighted adjacency, RA on a rebuilt multigraph) -> two_hop + ops.cn_aa."""
-    if adj.val is not None:
+    """(graph, weight table, sigmoid, use_values) of a heuristic filter model when it can take the fused
+    enumerate+score kernel (K6+K3, candidates.two_hop_scored): the scoring graph IS the graph whose 2-hop
+    neighbourhood defines the candidates and, if weighted (collab), its values are bitwise symmetric.
+    ``None`` otherwise (RA on a rebuilt multigraph) -> two_hop + ops.cn_aa."""
+    if not candidates.values_symmetric(adj):
         return None
     if model_name == "simple":
-        return adj, None, False                              # models.py:536-542
+        return adj, None, False, True                        # models.py:536-542 (weighted on collab)
     if model_name == "adamic":
-        return adj, adj.adamic_weights(), True               # models.py:544-554
+        return adj, adj.adamic_weights(), True, False        # models.py:544-554 (indices only)
     if model_name == "adamic_ogb":
-        return adj, adj.aa_ogb_weights(), False              # adamic_utils.py:13-25
-    if model_name == "resource_allocation" and (ra_adj is None or same_structure(ra_adj, adj)):
-        return adj, adj.ra_weights(), False                  # train_and_eval.py:195-216
+        return adj, adj.aa_ogb_weights(), False, True        # adamic_utils.py:13-25 (values of A)
+    if model_name == "resource_allocation" and adj.val is None and (ra_adj is None or same_structure(ra_adj, adj)):
+        return adj, adj.ra_weights(), False, True            # train_and_eval.py:195-216
     return None
 
 
@@ -173,7 +173,8 @@ def filter_topk(model_name: str, model, x, adj: SparseAdj, k: Optional[int] = No
         if fused is not None:
             # CN / AA / RA are the values of A@A: one walk over the owners' 2-paths yields the
             # candidates and their scores together (bit-identical to scoring the pairs with K3)
-            edges, score = candidates.two_hop_scored(fused[0], fused[1], lo, hi, sigmoid=fused[2], cap=cap)
+            edges, score = candidates.two_hop_scored(fused[0], fused[1], lo, hi, sigmoid=fused[2], cap=cap,
+                                                     use_values=fused[3])
         else:
             edges = candidates.two_hop(adj, lo, hi, cap=cap)
             if edges.shape[1]:

@@ -232,12 +232,16 @@ size_t eps_twohop_scored_workspace_bytes(int64_t N);
  *   offsets_out  int64[v_hi - v_lo + 1] (device): exclusive prefix of the
  *                real per-owner counts; offsets_out[last] = N <= cap, and the
  *                first N entries of the outputs are valid.
+ *   val          fp32[nnz] edge values or NULL (all ones).  With values (collab)
+ *                a 2-path v-k-u contributes A[u,k] * (A[v,k] * wtable[k]) (or
+ *                A[u,k] * A[v,k] without wtable) — eps_cn_aa's products; the
+ *                kernel reads A[k,u] for A[u,k], so A must be bitwise symmetric.
  *   wtable / flags / score / count as in eps_twohop_scored; score == NULL and
  *   count == NULL -> enumeration only (the GNN filter models).
  * Results are bit-identical to the two-pass entry points.
  * ------------------------------------------------------------------------- */
-int eps_twohop_onepass(const int32_t *rowptr, const int32_t *col, const float *wtable, int32_t n,
-                       int32_t v_lo, int32_t v_hi, const int64_t *bound_offsets, int64_t cap, int flags,
+int eps_twohop_onepass(const int32_t *rowptr, const int32_t *col, const float *val, const float *wtable,
+                       int32_t n, int32_t v_lo, int32_t v_hi, const int64_t *bound_offsets, int64_t cap, int flags,
                        int32_t *pair_u, int32_t *pair_v, float *score, int32_t *count,
                        int64_t *offsets_out, void *workspace, size_t workspace_bytes, void *stream);
 size_t eps_twohop_onepass_workspace_bytes(int64_t cap, int32_t n_owners);

@@ -268,12 +268,59 @@ def test_fused_twohop_scored_tiny_graphs():
         if cand.shape[1]:
             assert np.array_equal(cnt.cpu().numpy(), oh.cn_count_pairs(g, cand)), name
             assert np.array_equal(sc.cpu().numpy(), oh.aa_ogb_pairs(g, cand, order="exact")), name
-    # an empty owner range and a weighted graph (unsupported: must raise, not fall back)
+    # an empty owner range; a weighted graph with ASYMMETRIC values must raise, not fall back
     s, ei, w, g = synth_graph("tiny")
     adj = to_adj(g, DEV)
     e0, s0 = candidates.two_hop_scored(adj, None, 5, 5)
     assert e0.shape == (2, 0) and s0.numel() == 0
     from edge_proposal_sets_b200._lib import EpsError
+    g.val = np.random.default_rng(0).random(g.nnz).astype(np.float32) + 0.5
     adjw = to_adj(g, DEV, keep_values=True)
+    assert not candidates.values_symmetric(adjw)
     with pytest.raises(EpsError):
         candidates.two_hop_scored(adjw, None)
+    with pytest.raises(EpsError):                      # the two-pass kernels have no weighted variant
+        candidates.two_hop_scored(to_adj(synth_graph("tiny")[3], DEV, keep_values=True), None,
+                                  counts=candidates.owner_counts(adj))
+
+
+def test_fused_weighted_collab_equals_pairwise_kernel():
+    """collab keeps edge weights: the fused one-pass kernel forms A[u,k]*(A[v,k]*w_k) per 2-path and must
+    equal K3 (eps_cn_aa with values) and the oracle bit for bit — CN ('simple'), AA ('adamic_ogb'), and
+    the index-only 'adamic' variant; also through filter_topk."""
+    from edge_proposal_sets_b200 import candidates, filter_step, ops
+    s, ei, w, g = synth_graph("small", dataset="collab")
+    wts = np.random.default_rng(3).integers(1, 5, size=ei.shape[1] // 2).astype(np.float32)
+    g = og.add_edges("collab", ei, np.concatenate([wts, wts]), np.zeros((2, 0), np.int64), s["n"])
+    adj = to_adj(g, DEV)
+    assert adj.val is not None and candidates.values_symmetric(adj)
+    cand = og.two_hop_candidates(g)
+    wt = _dev(oh.aa_ogb_weights(g))
+    e, aa, cnt = candidates.two_hop_scored(adj, wt, want_count=True)
+    assert np.array_equal(e.cpu().numpy(), cand.astype(np.int32))
+    assert np.array_equal(cnt.cpu().numpy(), oh.cn_count_pairs(g, cand))
+    assert np.array_equal(aa.cpu().numpy(), oh.aa_ogb_pairs(g, cand, order="exact"))
+    assert torch.equal(aa, ops.cn_aa(adj, e, wt, use_values=True, grouped_by_v=True))
+    e2, cn = candidates.two_hop_scored(adj, None)                                 # weighted CN
+    assert np.array_equal(cn.cpu().numpy(), oh.cn_scores_pairs(g, cand))
+    assert torch.equal(cn, ops.cn_aa(adj, e, None, use_values=True, grouped_by_v=True))
+    e3, ad = candidates.two_hop_scored(adj, adj.adamic_weights(), sigmoid=True, use_values=False)
+    assert torch.equal(ad, ops.cn_aa(adj, e, adj.adamic_weights(), use_values=False, sigmoid=True, grouped_by_v=True))
+    # a non-integer but symmetric weighting (products round): still the same fp32 products as K3
+    key = np.minimum(np.repeat(np.arange(g.n), np.diff(g.rowptr)), g.col) * g.n + \
+        np.maximum(np.repeat(np.arange(g.n), np.diff(g.rowptr)), g.col)
+    uk, inv = np.unique(key, return_inverse=True)
+    g.val = (np.random.default_rng(9).random(uk.size).astype(np.float32) + 0.25)[inv]
+    adj2 = to_adj(g, DEV, keep_values=True)
+    assert candidates.values_symmetric(adj2)
+    wt2 = _dev(oh.aa_ogb_weights(g))
+    e4, aa4 = candidates.two_hop_scored(adj2, wt2)
+    assert torch.equal(aa4, ops.cn_aa(adj2, e4, wt2, use_values=True, grouped_by_v=True))
+    assert np.array_equal(aa4.cpu().numpy(), oh.aa_ogb_pairs(g, cand, order="exact"))
+    # filter_topk takes the fused path for the weighted graph and agrees with the oracle ranking
+    for model in ("simple", "adamic_ogb"):
+        assert filter_step.heuristic_table(model, adj) is not None
+    m = __import__("edge_proposal_sets_b200.models", fromlist=["x"]).CommonNeighborsPredictor(None, 0, None, None, None, None, model_type="adamic_ogb")
+    top = filter_step.filter_topk("adamic_ogb", m, None, adj, k=5000, slab_pairs=200000).cpu().numpy()
+    g1 = og.add_edges("collab", ei, np.concatenate([wts, wts]), np.zeros((2, 0), np.int64), s["n"])
+    assert np.array_equal(top, orank.sorted_edges(cand, oh.aa_ogb_pairs(g1, cand, order="exact"), 5000))
