@@ -36,7 +36,7 @@ SIGNATURES = {
     "eps_topk_f32": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     "eps_topk_workspace_bytes": (_sz, [_i64, _i64]),
     "eps_pack_edges": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
-    "eps_topk_select2_f32": (_int, [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "eps_topk_select2_f32": (_int, [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "eps_gather_pairs2": (_int, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "eps_twohop_candidates": (_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "eps_twohop_workspace_bytes": (_sz, []),

@@ -42,6 +42,20 @@ struct ScoreSrc {
   __device__ __forceinline__ float at(long long i) const {
     return i < na ? __ldg(a + i) : __ldg(b + (i - na));
   }
+  // elements i .. i+3 (those < M; the rest 0): one 128-bit load when the four lie in one segment and
+  // the address is 16-byte aligned, scalar loads otherwise (segment boundary, ragged end, odd offsets)
+  __device__ __forceinline__ void load4(long long i, long long M, float out[4]) const {
+    if (i + 3 < M && (i + 3 < na || i >= na)) {
+      const float *p = i >= na ? b + (i - na) : a + i;
+      if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+        out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+        return;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) out[q] = i + q < M ? at(i + q) : 0.f;
+  }
 };
 
 __device__ __forceinline__ uint32_t score_key(float s) {
@@ -63,37 +77,46 @@ __device__ __forceinline__ uint32_t pass_digit(uint32_t key) {
   return key & 0x3ffu;
 }
 
+// Lanes whose element cannot be the k-th (outside the prefix bucket of the earlier passes, or — pass 0 of a
+// running select — worse than the previous k-th key `prune_key`) do not take part.  MATCH.ANY is the
+// expensive instruction here (it paces the kernel at ~2 TB/s when issued per element), so it is only used
+// when many lanes take part (tie-heavy CN scores would serialise plain shared atomics); a warp with no
+// participant skips everything, one with a few issues plain atomics.
 template <int PASS>
 __global__ void __launch_bounds__(TK_THREADS)
 topk_hist_kernel(const ScoreSrc score, long long M, const TopkState *state,
-                 uint32_t *__restrict__ hist /*[2048]*/) {
+                 const uint32_t *__restrict__ prune_key, uint32_t *__restrict__ hist /*[2048]*/) {
   __shared__ uint32_t sh[2048];
   for (int i = threadIdx.x; i < 2048; i += TK_THREADS) sh[i] = 0;
   __syncthreads();
   const uint32_t prefix = PASS ? state->prefix : 0;
+  const uint32_t prune = (PASS == 0 && prune_key) ? *prune_key : 0xffffffffu;
   const int lane = lane_id();
-  const long long stride = (long long)gridDim.x * TK_THREADS;
-  // whole warps iterate together so the match below is convergent; four strided loads are issued
-  // before the first one is consumed
-  const long long start = (long long)blockIdx.x * TK_THREADS + threadIdx.x;
-  for (long long i = start; i - lane < M; i += 4 * stride) {
-    float sc[4];
+  const long long stride = (long long)gridDim.x * TK_THREADS * 4;
+  // whole warps iterate together (warp-uniform trip count); two 128-bit loads in flight per lane
+  const long long start = ((long long)blockIdx.x * TK_THREADS + threadIdx.x) * 4;
+  for (long long i = start; i - lane * 4 < M; i += 2 * stride) {
+    float sc[2][4];
+    score.load4(i, M, sc[0]);
+    score.load4(i + stride, M, sc[1]);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const long long j = i + q * stride;
-      sc[q] = j < M ? score.at(j) : 0.f;
-    }
+    for (int h = 0; h < 2; ++h) {
+      const long long j0 = i + h * stride;
+      if (j0 - lane * 4 >= M) break;                         // warp-uniform
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const long long j = i + q * stride;
-      if (j - lane >= M) break;                            // warp-uniform
-      const uint32_t key = score_key(sc[q]);
-      const bool ok = j < M && pass_match<PASS>(key, prefix);
-      // lanes that do not take part share ONE dummy id: match.any costs one round per distinct value
-      // in the warp, and in the later passes almost every lane is outside the prefix bucket
-      const uint32_t d = ok ? pass_digit<PASS>(key) : 0x10000u;
-      const unsigned peers = __match_any_sync(FULL, d);
-      if (ok && lane == (__ffs(peers) - 1)) atomicAdd(&sh[d], (uint32_t)__popc(peers));
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t key = score_key(sc[h][q]);
+        const bool ok = j0 + q < M && pass_match<PASS>(key, prefix) && key <= prune;
+        const unsigned part = __ballot_sync(FULL, ok);
+        if (part == 0) continue;
+        const uint32_t d = ok ? pass_digit<PASS>(key) : 0x10000u;
+        if (__popc(part) <= 8) {
+          if (ok) atomicAdd(&sh[d], 1u);
+        } else {
+          const unsigned peers = __match_any_sync(FULL, d);
+          if (ok && lane == (__ffs(peers) - 1)) atomicAdd(&sh[d], (uint32_t)__popc(peers));
+        }
+      }
     }
   }
   __syncthreads();
@@ -104,7 +127,8 @@ topk_hist_kernel(const ScoreSrc score, long long M, const TopkState *state,
 // one block of 256 threads: thread t owns bins [8t, 8t+8); block scan of the per-thread totals, then
 // the single thread whose range contains the k_rem-th element walks its eight bins
 template <int PASS>
-__global__ void __launch_bounds__(256) topk_pick_kernel(TopkState *state, const uint32_t *hist, uint32_t k) {
+__global__ void __launch_bounds__(256) topk_pick_kernel(TopkState *state, const uint32_t *hist, uint32_t k,
+                                                        uint32_t *kth_key_out) {
   constexpr int NB = (PASS == 2) ? 1024 : 2048;
   constexpr int PER = NB / 256;
   constexpr int SHIFT = (PASS == 0) ? 21 : (PASS == 1 ? 10 : 0);
@@ -139,7 +163,10 @@ __global__ void __launch_bounds__(256) topk_pick_kernel(TopkState *state, const 
     state->prefix = prefix | (d << SHIFT);
     state->k_rem = k_rem - cum;
     state->less_total = less + cum;
-    if (PASS == 2) state->need_eq = k_rem - cum;
+    if (PASS == 2) {
+      state->need_eq = k_rem - cum;
+      if (kth_key_out) *kth_key_out = prefix | (d << SHIFT);      // the k-th key: prune bound of the next select
+    }
   }
 }
 
@@ -149,12 +176,18 @@ topk_count_kernel(const ScoreSrc score, long long M, const TopkState *state,
   const uint32_t T = state->prefix;
   const long long base = (long long)blockIdx.x * TK_TILE;
   uint32_t nl = 0, ne = 0;
-  for (int t = threadIdx.x; t < TK_TILE; t += TK_THREADS) {
-    const long long i = base + t;
-    if (i < M) {
-      const uint32_t key = score_key(score.at(i));
-      nl += key < T;
-      ne += key == T;
+#pragma unroll
+  for (int t = 0; t < TK_TILE; t += TK_THREADS * 4) {
+    const long long i = base + t + threadIdx.x * 4;
+    float v[4];
+    score.load4(i, M, v);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (i + q < M) {
+        const uint32_t key = score_key(v[q]);
+        nl += key < T;
+        ne += key == T;
+      }
     }
   }
   __shared__ uint32_t sl[TK_THREADS / 32], se[TK_THREADS / 32];
@@ -288,12 +321,14 @@ topk_write_kernel(const ScoreSrc score, long long M, const TopkState *state,
     uint32_t key[4];
     uint32_t cls[4];  // 1 = less, 0x10000 = eq
     uint32_t mine = 0;
+    float v4[4];
+    score.load4(i0, M, v4);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const long long i = i0 + q;
       key[q] = 0; cls[q] = 0;
       if (i < M) {
-        key[q] = score_key(score.at(i));
+        key[q] = score_key(v4[q]);
         cls[q] = key[q] < T ? 1u : (key[q] == T ? 0x10000u : 0u);
       }
       mine += cls[q];
@@ -468,7 +503,8 @@ extern "C" size_t eps_topk_workspace_bytes(int64_t M, int64_t k) {
 
 namespace eps {
 // steps 1-3 (+ 4 when `sorted`) over the concatenation src = A ++ B of M elements
-static int topk_run(const ScoreSrc src, int64_t M, int64_t k, bool sorted, uint32_t *out_idx, float *out_score,
+static int topk_run(const ScoreSrc src, int64_t M, int64_t k, bool sorted, const uint32_t *prune_key,
+                    uint32_t *kth_key_out, uint32_t *out_idx, float *out_score,
                     void *workspace, size_t workspace_bytes, cudaStream_t stream, const char *who) {
   const int sms = sm_count();
   if (sms <= 0) { set_error("%s: no CUDA device", who); return EPS_ERR_CUDA; }
@@ -489,12 +525,12 @@ static int topk_run(const ScoreSrc src, int64_t M, int64_t k, bool sorted, uint3
   EPS_CUDA(cudaMemsetAsync(ws + L.state, 0, L.blk_less - L.state, stream));  // state + hist
   const long long want = (M + TK_THREADS * 8 - 1) / (TK_THREADS * 8);
   const int hgrid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sms * 8));
-  topk_hist_kernel<0><<<hgrid, TK_THREADS, 0, stream>>>(src, M, state, hist);
-  topk_pick_kernel<0><<<1, 256, 0, stream>>>(state, hist, (uint32_t)k);
-  topk_hist_kernel<1><<<hgrid, TK_THREADS, 0, stream>>>(src, M, state, hist + 2048);
-  topk_pick_kernel<1><<<1, 256, 0, stream>>>(state, hist + 2048, (uint32_t)k);
-  topk_hist_kernel<2><<<hgrid, TK_THREADS, 0, stream>>>(src, M, state, hist + 4096);
-  topk_pick_kernel<2><<<1, 256, 0, stream>>>(state, hist + 4096, (uint32_t)k);
+  topk_hist_kernel<0><<<hgrid, TK_THREADS, 0, stream>>>(src, M, state, prune_key, hist);
+  topk_pick_kernel<0><<<1, 256, 0, stream>>>(state, hist, (uint32_t)k, nullptr);
+  topk_hist_kernel<1><<<hgrid, TK_THREADS, 0, stream>>>(src, M, state, nullptr, hist + 2048);
+  topk_pick_kernel<1><<<1, 256, 0, stream>>>(state, hist + 2048, (uint32_t)k, nullptr);
+  topk_hist_kernel<2><<<hgrid, TK_THREADS, 0, stream>>>(src, M, state, nullptr, hist + 4096);
+  topk_pick_kernel<2><<<1, 256, 0, stream>>>(state, hist + 4096, (uint32_t)k, kth_key_out);
   EPS_LAUNCH_CHECK();
   topk_count_kernel<<<L.nblk, TK_THREADS, 0, stream>>>(src, M, state, blk_less, blk_eq);
   scan_exclusive(blk_less, blk_eq, (long long)L.nblk, scan_tmp, stream);
@@ -525,12 +561,13 @@ extern "C" int eps_topk_f32(const float *score, int64_t M, int64_t k, uint32_t *
   EPS_CHECK_ARG(out_idx || out_score, "no output requested");
   EPS_CHECK_ARG(M >= 1 && M < 0xffffffffll, "M out of range [1, 2^32-1)");
   EPS_CHECK_ARG(k >= 1 && k <= M, "k out of range [1, M]");
-  return topk_run(ScoreSrc{nullptr, 0, score}, M, k, true, out_idx, out_score, workspace, workspace_bytes,
-                  (cudaStream_t)stream_, "eps_topk_f32");
+  return topk_run(ScoreSrc{nullptr, 0, score}, M, k, true, nullptr, nullptr, out_idx, out_score, workspace,
+                  workspace_bytes, (cudaStream_t)stream_, "eps_topk_f32");
 }
 
 extern "C" int eps_topk_select2_f32(const float *score_a, int64_t Ma, const float *score_b, int64_t Mb,
-                                    int64_t k, uint32_t *out_idx, float *out_score, void *workspace,
+                                    int64_t k, const uint32_t *prune_key, uint32_t *kth_key_out,
+                                    uint32_t *out_idx, float *out_score, void *workspace,
                                     size_t workspace_bytes, void *stream_) {
   using namespace eps;
   EPS_CHECK_ARG(Ma >= 0 && Mb >= 0 && (Ma == 0 || score_a) && (Mb == 0 || score_b), "bad segments");
@@ -538,8 +575,8 @@ extern "C" int eps_topk_select2_f32(const float *score_a, int64_t Ma, const floa
   const int64_t M = Ma + Mb;
   EPS_CHECK_ARG(M >= 1 && M < 0xffffffffll, "Ma + Mb out of range [1, 2^32-1)");
   EPS_CHECK_ARG(k >= 1 && k <= M, "k out of range [1, Ma + Mb]");
-  return topk_run(ScoreSrc{score_a, Ma, score_b}, M, k, false, out_idx, out_score, workspace, workspace_bytes,
-                  (cudaStream_t)stream_, "eps_topk_select2_f32");
+  return topk_run(ScoreSrc{score_a, Ma, score_b}, M, k, false, prune_key, kth_key_out, out_idx, out_score,
+                  workspace, workspace_bytes, (cudaStream_t)stream_, "eps_topk_select2_f32");
 }
 
 extern "C" int eps_gather_pairs2(const int32_t *ua, const int32_t *va, int64_t Ma, const int32_t *ub,

@@ -326,27 +326,75 @@ owner_scan_kernel(const unsigned int *__restrict__ counts, int n_own, long long 
   if (t == 1023) offsets[n_own] = (long long)part[1023];
 }
 
-// padded slot of owner v -> compact position; fixed-point sums -> fp32 scores on the way
-__global__ void __launch_bounds__(256)
+// padded slot of owner v -> compact position; fixed-point sums -> fp32 scores on the way.
+// Work is cut by COMPACT position (tiles of CP_TILE candidates), not by owner, so a hub with 10^5
+// candidates does not serialise on one CTA; the owner of a position is found by binary search over the
+// compact offsets of the (few) owners the tile touches.
+constexpr int CP_THREADS = 256, CP_PER = 8, CP_TILE = CP_THREADS * CP_PER;
+
+__global__ void __launch_bounds__(CP_THREADS)
 twohop_compact_kernel(const long long *__restrict__ pad_off, const long long *__restrict__ cmp_off,
                       int v_lo, int n_own, long long cap, const int *__restrict__ pad_u,
                       const unsigned long long *__restrict__ acc, const int *__restrict__ cn, int flags,
                       int *__restrict__ pair_u, int *__restrict__ pair_v, float *__restrict__ score,
                       int *__restrict__ count) {
-  if (cmp_off[n_own] > cap) return;     // a violated bound poisoned N: the caller reports it, nothing is moved
-  for (int o = blockIdx.x; o < n_own; o += gridDim.x) {
-    const long long src = pad_off[o], dst = cmp_off[o];
-    const int cnt = (int)(cmp_off[o + 1] - dst);
-    const int v = v_lo + o;
-    for (int i = threadIdx.x; i < cnt; i += 256) {
-      pair_u[dst + i] = pad_u[src + i];
-      pair_v[dst + i] = v;
-      if (score) {
-        float sc = acc ? from_fixed(acc[src + i]) : (float)cn[src + i];
-        if (flags & EPS_CN_SIGMOID) sc = sigmoidf_ref(sc);
-        score[dst + i] = sc;
+  const long long N = cmp_off[n_own];
+  if (N > cap) return;     // a violated bound poisoned N: the caller reports it, nothing is moved
+  __shared__ int s_lo, s_hi;
+  const long long ntiles = (N + CP_TILE - 1) / CP_TILE;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long base = tile * CP_TILE, end = min(base + (long long)CP_TILE, N);
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      // largest o with cmp_off[o] <= x  (x = first / last position of the tile)
+      const long long x = threadIdx.x == 0 ? base : end - 1;
+      int lo = 0, hi = n_own;                       // invariant: cmp_off[lo] <= x < cmp_off[hi]
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (cmp_off[mid] <= x) lo = mid; else hi = mid;
       }
-      if (count) count[dst + i] = cn[src + i];
+      if (threadIdx.x == 0) s_lo = lo; else s_hi = lo;
+    }
+    __syncthreads();
+    const int o_lo = s_lo, o_hi = s_hi;
+    long long src[CP_PER];
+    int own[CP_PER];
+#pragma unroll
+    for (int q = 0; q < CP_PER; ++q) {
+      const long long i = base + q * CP_THREADS + threadIdx.x;
+      int lo = o_lo, hi = o_hi + 1;
+      if (i < end) {
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (cmp_off[mid] <= i) lo = mid; else hi = mid;
+        }
+      }
+      own[q] = lo;
+      src[q] = i < end ? pad_off[lo] + (i - cmp_off[lo]) : -1;
+    }
+    int uu[CP_PER], cc[CP_PER];
+    unsigned long long aa[CP_PER];
+#pragma unroll
+    for (int q = 0; q < CP_PER; ++q) {
+      uu[q] = 0; cc[q] = 0; aa[q] = 0ull;
+      if (src[q] >= 0) {
+        uu[q] = pad_u[src[q]];
+        if (acc) aa[q] = acc[src[q]];
+        if (cn) cc[q] = cn[src[q]];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < CP_PER; ++q) {
+      if (src[q] < 0) continue;
+      const long long i = base + q * CP_THREADS + threadIdx.x;
+      pair_u[i] = uu[q];
+      pair_v[i] = v_lo + own[q];
+      if (score) {
+        float sc = acc ? from_fixed(aa[q]) : (float)cc[q];
+        if (flags & EPS_CN_SIGMOID) sc = sigmoidf_ref(sc);
+        score[i] = sc;
+      }
+      if (count) count[i] = cc[q];
     }
   }
 }
@@ -484,8 +532,8 @@ extern "C" int eps_twohop_onepass(const int32_t *rowptr, const int32_t *col, con
   owner_scan_kernel<<<1, 1024, 0, stream>>>(counts, n_own, (long long *)offsets_out);
   EPS_LAUNCH_CHECK();
   if (cap > 0) {
-    const int cgrid = (int)std::min<long long>((long long)n_own, (long long)sms * 8);
-    twohop_compact_kernel<<<cgrid, 256, 0, stream>>>((const long long *)bound_offsets,
+    const int cgrid = (int)std::min<long long>((cap + CP_TILE - 1) / CP_TILE, (long long)sms * 8);
+    twohop_compact_kernel<<<cgrid, CP_THREADS, 0, stream>>>((const long long *)bound_offsets,
                                                      (const long long *)offsets_out, v_lo, n_own, (long long)cap,
                                                      pad_u, acc,
                                                      cn, flags, pair_u, pair_v, score, count);

@@ -128,6 +128,7 @@ class RunningTopK:
     def __init__(self, k: Optional[int]):
         self.k = k                      # None: keep every candidate, like the reference
         self.u = self.v = self.score = None
+        self.kth_key = None             # order key of the current k-th score (device), once the list is full
         self.seen = 0
 
     def update(self, edges: torch.Tensor, score: torch.Tensor) -> None:
@@ -146,7 +147,9 @@ class RunningTopK:
                 self.u, self.v = torch.cat([self.u, pu]), torch.cat([self.v, pv])
                 self.score = torch.cat([self.score, score])
             return
-        idx, sc = ops.topk_select2(self.score, score, kk)
+        # a full list lets the select skip every slab element that is already worse than its k-th score
+        prune = self.kth_key if (have == kk and self.kth_key is not None) else None
+        idx, sc, self.kth_key = ops.topk_select2(self.score, score, kk, prune_key=prune, want_kth_key=True)
         self.u, self.v = ops.gather_pairs2(None if self.score is None else (self.u, self.v), (pu, pv), idx)
         self.score = sc
 

@@ -170,10 +170,13 @@ def topk_edges(edges: torch.Tensor, score: torch.Tensor, k: int) -> torch.Tensor
     return out
 
 
-def topk_select2(score_a: Optional[torch.Tensor], score_b: torch.Tensor, k: int):
+def topk_select2(score_a: Optional[torch.Tensor], score_b: torch.Tensor, k: int,
+                 prune_key: Optional[torch.Tensor] = None, want_kth_key: bool = False):
     """K4 steps 1-3 over the virtual concatenation ``score_a ++ score_b``: (virtual positions int32 [k]
-    ascending, scores fp32 [k]) of the k best, ties by position.  No sort (see ``RunningTopK``)."""
-    _need_cuda(score_a, score_b)
+    ascending, scores fp32 [k]) of the k best, ties by position.  No sort (see ``RunningTopK``).
+    ``prune_key`` (int32 [1] device: the k-th key returned by the previous call whose result is
+    ``score_a``) lets pass 0 skip elements that are already out; ``want_kth_key`` returns this call's."""
+    _need_cuda(score_a, score_b, prune_key)
     lib = _lib.load()
     Ma = 0 if score_a is None else score_a.numel()
     Mb = score_b.numel()
@@ -182,13 +185,14 @@ def topk_select2(score_a: Optional[torch.Tensor], score_b: torch.Tensor, k: int)
     k = min(int(k), Ma + Mb)
     idx = torch.empty(k, dtype=torch.int32, device=score_b.device)
     out = torch.empty(k, dtype=torch.float32, device=score_b.device)
+    kth = torch.empty(1, dtype=torch.int32, device=score_b.device) if want_kth_key else None
     if k == 0:
-        return idx, out
+        return (idx, out, kth) if want_kth_key else (idx, out)
     ws = _ws(lib.eps_topk_workspace_bytes(Ma + Mb, k), score_b.device)
-    check(lib.eps_topk_select2_f32(_ptr(score_a), Ma, _ptr(score_b), Mb, k, _ptr(idx), _ptr(out), _ptr(ws),
-                                   ws.numel(), _stream()), "eps_topk_select2_f32")
+    check(lib.eps_topk_select2_f32(_ptr(score_a), Ma, _ptr(score_b), Mb, k, _ptr(prune_key), _ptr(kth), _ptr(idx),
+                                   _ptr(out), _ptr(ws), ws.numel(), _stream()), "eps_topk_select2_f32")
     LAUNCHES["n"] += _SELECT_LAUNCHES
-    return idx, out
+    return (idx, out, kth) if want_kth_key else (idx, out)
 
 
 def gather_pairs2(pairs_a, pairs_b, idx: torch.Tensor):

@@ -162,12 +162,16 @@ int eps_pack_edges(const int32_t *pair_u, const int32_t *pair_v, const uint32_t 
  *     best (ties by position) in ASCENDING POSITION order, out_score[k] their
  *     scores.  Position order is all the next call needs, so the running list
  *     is sorted only once, at the end (eps_topk_f32 with k == M).
+ *     kth_key_out (device uint32, optional) receives the order key of the k-th
+ *     selected score; passed back as prune_key to the NEXT call (valid only when
+ *     score_a is that call's full k-element result) it lets the first histogram
+ *     pass skip every element that is already worse than the running k-th.
  *   eps_gather_pairs2: (u, v) of those positions from the two pair segments.
  * Workspace: eps_topk_workspace_bytes(Ma + Mb, k).
  * ------------------------------------------------------------------------- */
 int eps_topk_select2_f32(const float *score_a, int64_t Ma, const float *score_b, int64_t Mb, int64_t k,
-                         uint32_t *out_idx, float *out_score, void *workspace, size_t workspace_bytes,
-                         void *stream);
+                         const uint32_t *prune_key, uint32_t *kth_key_out, uint32_t *out_idx,
+                         float *out_score, void *workspace, size_t workspace_bytes, void *stream);
 int eps_gather_pairs2(const int32_t *ua, const int32_t *va, int64_t Ma, const int32_t *ub,
                       const int32_t *vb, const uint32_t *idx, int64_t k, int32_t *out_u, int32_t *out_v,
                       void *stream);
