@@ -184,7 +184,9 @@ static size_t tc_img_bytes(int H, int L) {
 }
 
 size_t linkpred_tc_workspace_bytes(int n, int H, int L, long long M) {
-  return 256 + tc_img_bytes(H, L) + (linkpred_tc_uses_table(n, M) ? (size_t)n * H * 2 : 0);
+  // weight images | bf16 embedding table | tile schedule of the pipelined kernel (one int per 256 pairs)
+  return 256 + tc_img_bytes(H, L) + (linkpred_tc_uses_table(n, M) ? (((size_t)n * H * 2 + 255) & ~(size_t)255) : 0) +
+         (size_t)((M + 255) / 256) * 4 + 256;
 }
 
 template <int H>
@@ -219,12 +221,14 @@ int linkpred_tc_launch(const float *h, int n, int H, const int *pu, const int *p
   const char *variant = getenv("EPS_TC_VARIANT");
   if (!(variant && variant[0] == '1') && sm_count() >= 2) {
     void *table = nullptr;
+    uint8_t *tail = img + ((tc_img_bytes(H, L) + 255) & ~(size_t)255);
     if (linkpred_tc_uses_table(n, M) && !(variant && variant[0] == '2')) {
-      table = img + tc_img_bytes(H, L);
+      table = tail;
+      tail += ((size_t)n * H * 2 + 255) & ~(size_t)255;
       const int st = h_to_bf16_launch(h, (long long)n * H, table, stream);
       if (st != EPS_OK) return st;
     }
-    return linkpred_tc2_launch(h, table, H, pu, pv, M, prm, L, apply_sigmoid, score, img, stream);
+    return linkpred_tc2_launch(h, table, H, pu, pv, M, prm, L, apply_sigmoid, score, img, n, (int *)tail, stream);
   }
   const int total = (L - 1) * H * (H / 8);
   pack_weights_kernel<<<(total + 255) / 256, 256, 0, stream>>>(prm, H, L - 1, img);

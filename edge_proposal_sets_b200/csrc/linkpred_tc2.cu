@@ -207,15 +207,17 @@ static int tc2_launch_h(const float *h, const int *pu, const int *pv, long long 
 }
 
 int linkpred_tc2_launch(const float *h, const void *h_bf16, int H, const int *pu, const int *pv, long long M,
-                        const MlpParams &prm, int L, int apply_sigmoid, float *score, uint8_t *img,
-                        cudaStream_t stream) {
+                        const MlpParams &prm, int L, int apply_sigmoid, float *score, uint8_t *img, int n,
+                        int *tile_order, cudaStream_t stream) {
   const int total = (L - 1) * H * (H / 8);
   pack_weights_halves_kernel<<<(total + 255) / 256, 256, 0, stream>>>(prm, H, L - 1, img);
   EPS_LAUNCH_CHECK();
   const char *variant = getenv("EPS_TC_VARIANT");   // "2": force this (unpipelined) kernel
   if (!(variant && variant[0] == '2')) {
-    const int st = h_bf16 ? linkpred_tc3_launch(h_bf16, 1, H, pu, pv, M, prm, L, apply_sigmoid, score, img, stream)
-                          : linkpred_tc3_launch(h, 0, H, pu, pv, M, prm, L, apply_sigmoid, score, img, stream);
+    const int st = h_bf16 ? linkpred_tc3_launch(h_bf16, 1, H, pu, pv, M, prm, L, apply_sigmoid, score, img, n,
+                                                tile_order, stream)
+                          : linkpred_tc3_launch(h, 0, H, pu, pv, M, prm, L, apply_sigmoid, score, img, n,
+                                                tile_order, stream);
     if (st != EPS_ERR_UNSUPPORTED) return st;       // pipelined kernel ran (or failed for real)
   }
   if (H == 64) return tc2_launch_h<64>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, stream);

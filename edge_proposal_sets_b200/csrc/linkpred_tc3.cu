@@ -192,7 +192,8 @@ template <int H, bool HB /* h is a bf16 table (else fp32) */, int NG /* producer
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(p_maxreg(NG))
 linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, const int *__restrict__ pv,
                     long long M, const MlpParams prm, int L, int apply_sigmoid,
-                    const uint8_t *__restrict__ wimg, float *__restrict__ score, int tune, int ring) {
+                    const uint8_t *__restrict__ wimg, float *__restrict__ score, int tune, int ring,
+                    const int *__restrict__ tile_order) {
   static_assert(H % 64 == 0 && H >= 64 && H <= 256, "H in {64,128,192,256}");
   constexpr int HH = H / 2;
   constexpr int WH_BYTES = HH * H * 2;
@@ -301,7 +302,9 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
       const int nj = (G == 2 && tile0 + nclusters < npair_tiles) ? 2 : 1;
       for (int l = 0; l < nhidden; ++l)
       for (int tj = 0; tj < nj; ++tj) {
-        const long long p0 = (tile0 + tj * nclusters) * (2 * TC_BM) + (long long)cta_rank * TC_BM;
+        const long long sched = tile0 + tj * nclusters;       // schedule slot -> pair tile (u-block order)
+        const long long p0 = (tile_order ? (long long)__ldg(tile_order + sched) : sched) * (2 * TC_BM) +
+                             (long long)cta_rank * TC_BM;
         const uint32_t slot = G == 2 ? (uint32_t)tj : (seq++ & 1u);
         mbar_wait_cluster(smem_u32(&bars.acc_full[slot]), (acph >> slot) & 1u);
         acph ^= 1u << slot;
@@ -487,7 +490,8 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
     for (long long tile = cluster_id; tile < npair_tiles; tile += nclusters, ++tl) {
       const int slot = (int)(tl & 1);
       mbar_wait_cluster(smem_u32(&bars.ids_empty[slot]), (uint32_t)(((tl >> 1) & 1) ^ 1));
-      const long long p0 = tile * (2 * TC_BM) + (long long)cta_rank * TC_BM;
+      const long long p0 = (tile_order ? (long long)__ldg(tile_order + tile) : tile) * (2 * TC_BM) +
+                           (long long)cta_rank * TC_BM;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int r = lane + 32 * q;
@@ -660,9 +664,68 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
   }
 }
 
+// ---- L2-aware tile schedule -------------------------------------------------------------------------
+// The pair list is owner-major with u ascending inside an owner, so consecutive tiles sweep the whole
+// embedding table (295 MB of bf16 rows on the ppa shape, 2.3x the L2) once per owner and the row gathers
+// hit L2 only ~50 % of the time.  Scores are written by pair index, so the ORDER in which tiles are
+// processed is free: tiles are scheduled u-block by u-block (block = a node range whose rows fit the L2
+// budget), owners ascending inside a block — every row is then fetched from HBM about once per block
+// instead of once per owner.  tile_order[slot] = pair tile; a stable counting sort by the block of the
+// tile's first u (one CTA; a few hundred thousand tiles).  An experiment knob, see tc3_ublock_nodes.
+constexpr int TO_THREADS = 256, TO_MAX_BLOCKS = 32;     // 33 KB of static shared memory
+
+__global__ void __launch_bounds__(TO_THREADS)
+tile_order_kernel(const int *__restrict__ pu, long long M, long long ntiles, int tile_pairs, int block_nodes,
+                  int nblocks, int *__restrict__ order) {
+  __shared__ int cnt[TO_MAX_BLOCKS][TO_THREADS + 1];
+  const int t = threadIdx.x;
+  const long long per = (ntiles + TO_THREADS - 1) / TO_THREADS;
+  const long long lo = min(ntiles, (long long)t * per), hi = min(ntiles, lo + per);
+  for (int b = 0; b < nblocks; ++b) cnt[b][t] = 0;
+  for (long long i = lo; i < hi; ++i) cnt[min(__ldg(pu + i * tile_pairs) / block_nodes, nblocks - 1)][t]++;
+  __syncthreads();
+  // exclusive scan in (block, thread) order: thread b*... a single warp per block row is plenty
+  __shared__ int base[TO_MAX_BLOCKS + 1];
+  if (t < nblocks) {
+    int run = 0;
+    for (int j = 0; j < TO_THREADS; ++j) { const int c = cnt[t][j]; cnt[t][j] = run; run += c; }
+    cnt[t][TO_THREADS] = run;
+  }
+  __syncthreads();
+  if (t == 0) {
+    int run = 0;
+    for (int b = 0; b < nblocks; ++b) { base[b] = run; run += cnt[b][TO_THREADS]; }
+  }
+  __syncthreads();
+  int pos[TO_MAX_BLOCKS];
+#pragma unroll 1
+  for (int b = 0; b < nblocks; ++b) pos[b] = base[b] + cnt[b][t];
+  for (long long i = lo; i < hi; ++i) {
+    const int b = min(__ldg(pu + i * tile_pairs) / block_nodes, nblocks - 1);
+    order[pos[b]++] = (int)i;
+  }
+}
+
+// node-range size whose embedding rows fit the L2 budget; 0 = keep the natural order
+int tc3_ublock_nodes(int n, int row_bytes, long long M) {
+  // OFF by default: measured on the ppa shape (profiles/round1_e_k2_tile_schedule.md) the schedule does not
+  // pay — 64.9 ms per 4 slabs in natural order vs 65.7 / 66.7 / 66.6 / 68.3 ms with 32 / 48 / 64 / 96 MB
+  // blocks: the id warp's L2 prefetch already hides the misses, and blocking gives up the h[v] reuse of
+  // long owner runs.  EPS_TC3_UBLOCK_MB=<MB> switches it on for A/B runs.
+  int mb = 0;
+  if (const char *e = getenv("EPS_TC3_UBLOCK_MB")) mb = atoi(e);
+  if (mb <= 0) return 0;
+  const long long table = (long long)n * row_bytes, budget = (long long)mb << 20;
+  if (table <= budget || M < 8ll * n) return 0;          // table already L2-resident / too few pairs per row
+  long long nb = (table + budget - 1) / budget;
+  if (nb > TO_MAX_BLOCKS) nb = TO_MAX_BLOCKS;
+  return (int)((n + nb - 1) / nb);
+}
+
 template <int H, bool HB, int NG>
 static int tc3_launch_g(const void *h, const int *pu, const int *pv, long long M, const MlpParams &prm, int L,
-                        int apply_sigmoid, float *score, uint8_t *img, cudaStream_t stream) {
+                        int apply_sigmoid, float *score, uint8_t *img, int n, int *tile_order,
+                        cudaStream_t stream) {
   const int nhidden = L - 1;
   const size_t fixed = (size_t)nhidden * (H / 2) * H * 2 + (nhidden >= 2 ? (size_t)P_A2_SLOTS * TC_BM * 128 : 0) +
                        (size_t)TC_BM * 32 + (size_t)nhidden * (H / 2) * 32 +          // bias K-step tiles
@@ -679,7 +742,14 @@ static int tc3_launch_g(const void *h, const int *pu, const int *pv, long long M
   const int clusters = (int)std::min<long long>(npair_tiles, (long long)(sm_count() / 2));
   const char *tn = getenv("EPS_TC3_TUNE");   // bit0: L2 row prefetch by the id warp (default on)
   const int tune = tn ? atoi(tn) : 1;
-  kern<<<2 * clusters, p_threads(NG), smem, stream>>>(h, pu, pv, M, prm, L, apply_sigmoid, img, score, tune, ring);
+  const int block_nodes = tile_order ? tc3_ublock_nodes(n, H * (HB ? 2 : 4), M) : 0;
+  if (block_nodes > 0) {
+    const int nblocks = (n + block_nodes - 1) / block_nodes;
+    tile_order_kernel<<<1, TO_THREADS, 0, stream>>>(pu, M, npair_tiles, 2 * TC_BM, block_nodes, nblocks, tile_order);
+    EPS_LAUNCH_CHECK();
+  }
+  kern<<<2 * clusters, p_threads(NG), smem, stream>>>(h, pu, pv, M, prm, L, apply_sigmoid, img, score, tune, ring,
+                                                     block_nodes > 0 ? tile_order : nullptr);
   EPS_LAUNCH_CHECK();
 #ifdef EPS_TC3_TRACE
   if (const char *tf = getenv("EPS_TC3_TRACE_FILE")) {
@@ -696,11 +766,12 @@ static int tc3_launch_g(const void *h, const int *pu, const int *pv, long long M
 
 template <int H, bool HB>
 static int tc3_launch_h(const void *h, const int *pu, const int *pv, long long M, const MlpParams &prm, int L,
-                        int apply_sigmoid, float *score, uint8_t *img, cudaStream_t stream) {
+                        int apply_sigmoid, float *score, uint8_t *img, int n, int *tile_order, cudaStream_t stream) {
   // producer groups: 2 (default: 14 warps -> 128 registers, nothing spills) or 3 (18 warps -> 96 registers)
   const char *g = getenv("EPS_TC3_GROUPS");
-  if (g && g[0] == '3') return tc3_launch_g<H, HB, 3>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, stream);
-  return tc3_launch_g<H, HB, 2>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, stream);
+  if (g && g[0] == '3')
+    return tc3_launch_g<H, HB, 3>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, n, tile_order, stream);
+  return tc3_launch_g<H, HB, 2>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, n, tile_order, stream);
 }
 
 // fp32 embeddings -> bf16 table (round to nearest even), 8 elements per thread
@@ -728,11 +799,11 @@ int h_to_bf16_launch(const float *h, long long elems, void *out, cudaStream_t st
 // expects the per-half weight images of pack_weights_halves_kernel (linkpred_tc2.cu) in `img`;
 // h_is_bf16: `h` is the bf16 table written by h_to_bf16_launch, else the caller's fp32 matrix
 int linkpred_tc3_launch(const void *h, int h_is_bf16, int H, const int *pu, const int *pv, long long M,
-                        const MlpParams &prm, int L, int apply_sigmoid, float *score, uint8_t *img,
-                        cudaStream_t stream) {
-#define EPS_TC3(HV)                                                                                       \
-  return h_is_bf16 ? tc3_launch_h<HV, true>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, stream)      \
-                   : tc3_launch_h<HV, false>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, stream)
+                        const MlpParams &prm, int L, int apply_sigmoid, float *score, uint8_t *img, int n,
+                        int *tile_order, cudaStream_t stream) {
+#define EPS_TC3(HV)                                                                                                      \
+  return h_is_bf16 ? tc3_launch_h<HV, true>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, n, tile_order, stream)      \
+                   : tc3_launch_h<HV, false>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, n, tile_order, stream)
   if (H == 64) { EPS_TC3(64); }
   if (H == 128) { EPS_TC3(128); }
   EPS_TC3(256);

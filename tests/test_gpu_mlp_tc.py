@@ -90,3 +90,29 @@ def test_tc_arm_score_is_a_function_of_the_pair_only(H, L):
     for lo, hi in [(0, 5000), (12345, 12345 + 777), (M - 300, M)]:      # M' < 2n: fp32-source path
         part = ops.linkpred_mlp(hd, ed[:, lo:hi].contiguous(), Ws, bs, "bf16", sigmoid=False)
         assert torch.equal(part, full[lo:hi])
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("H,L,M", [(256, 3, 300001), (128, 2, 77777), (64, 2, 262144)])
+def test_tc_arm_l2_tile_schedule_is_order_free(H, L, M):
+    """The u-block tile schedule (csrc/linkpred_tc3.cu, tile_order_kernel) only permutes the ORDER in which
+    256-pair tiles are processed; every score must keep its bits and its place.  Forced on with a 1 MB
+    block budget (the default 48 MB budget switches it on only for tables larger than L2)."""
+    import os
+    from edge_proposal_sets_b200 import ops
+    n = 6000
+    sd, h, e, Ws, bs = _setup(H, L, n, M, seed=7)
+    # owner-major list with ascending u inside an owner, like the candidate slabs
+    order = np.lexsort((e[0], e[1]))
+    e = e[:, order]
+    hd, ed = torch.from_numpy(h).to(DEV), torch.from_numpy(e).to(DEV)
+    os.environ["EPS_TC3_UBLOCK_MB"] = "0"
+    try:
+        natural = ops.linkpred_mlp(hd, ed, Ws, bs, "bf16").cpu().numpy()
+        os.environ["EPS_TC3_UBLOCK_MB"] = "1"
+        blocked = ops.linkpred_mlp(hd, ed, Ws, bs, "bf16").cpu().numpy()
+    finally:
+        os.environ.pop("EPS_TC3_UBLOCK_MB", None)
+    assert np.array_equal(natural, blocked)
+    want = ognn.linkpred_forward(torch.from_numpy(h), e, sd, L, torch.float64).numpy()
+    assert np.max(np.abs(blocked - want)) <= 2e-3
