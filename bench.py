@@ -466,11 +466,11 @@ def run_b200(args):
         del edges0, cnt0, dd
     mean_du_dv = sum_dudv / M
     # the fused K6+K3 kernel walks the owners' 2-paths twice (mark, score) instead of two lists per
-    # pair: 2 x 4 B per 2-path + 4 B per N(v) entry x 3 + per candidate 8 B pair + 8 B fixed-point
-    # accumulator (zero, RED, read) + 4 B count + 4 B score out
+    # pair: 2 x 4 B per 2-path; per candidate the padded slot (u 4 B, fixed-point sum 8 B zero + 8 B RED,
+    # count 4 + 4 B) and the compaction (16 B read, 16 B written: u, v, score, count)
     work = candidates.two_path_work(adj)
     twopaths = int(sum(int(work[a:b].sum().item()) for a, b in slabs))
-    fused_bytes = (8 if adj.val is None else 12) * twopaths + 28 * M    # weighted: + the value next to u
+    fused_bytes = (8 if adj.val is None else 12) * twopaths + 60 * M    # weighted: + the value next to u
     mlp_flops = M * (2 * H * H * (L - 1) + 3 * H)
     mlp_bytes = M * (2 * H * 4 + 12)
     nnz_hat = int(h_col.numel()) + n                          # GCN adds the self loops
@@ -566,8 +566,12 @@ def run_b200(args):
             if mlp_arm == "fp32" else
             roof_entry("linkpred_tc3_kernel (K2 tcgen05, cta_group::2)", "tensor", mlp_flops, phase_ms["mlp"], S, "linkpred_tc3",
                        "phase = bf16 table conversion + weight packing + the kernel"),
-            "cn_aa": roof_entry("twohop_score_kernel (K6+K3 fused)" if fused else "cn_grouped_kernel (K3)", "hbm",
-                                k3_bytes, phase_ms["cn_aa"], S, "twohop_score" if fused else "cn_grouped",
+            "topk": roof_entry("topk_hist/count/write kernels (K4 running select, both models)", "hbm",
+                               2 * (4 * M + 12 * k * S), phase_ms["topk"], 2 * S, "topk",
+                               "algorithmic bytes = one read of the slab's scores + 12 B per kept row (SURVEY 8d) per select; "
+                               "the radix select reads the scores 5x and the phase includes the two final sorts"),
+            "cn_aa": roof_entry("twohop_score_kernel + twohop_compact_kernel (K6+K3 fused, one pass)" if fused else "cn_grouped_kernel (K3)", "hbm",
+                                k3_bytes, phase_ms["cn_aa"], S, "twohop_onepass" if fused else "cn_grouped",
                                 "algorithmic bytes = the pair-by-pair figure 4(d_u+d_v)+12 of SURVEY 8d; the fused kernel "
                                 f"walks 2-paths instead and moves ~{fused_bytes / S / 1e9:.2f} GB per launch "
                                 f"({fused_bytes / S / (phase_ms['cn_aa'] / S * 1e-3) / 1e9:.0f} GB/s of its own traffic model)"

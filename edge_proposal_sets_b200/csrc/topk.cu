@@ -103,10 +103,19 @@ topk_hist_kernel(const ScoreSrc score, long long M, const TopkState *state,
     for (int h = 0; h < 2; ++h) {
       const long long j0 = i + h * stride;
       if (j0 - lane * 4 >= M) break;                         // warp-uniform
+      uint32_t keys[4];
+      bool oks[4], any_ok = false;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const uint32_t key = score_key(sc[h][q]);
-        const bool ok = j0 + q < M && pass_match<PASS>(key, prefix) && key <= prune;
+        keys[q] = score_key(sc[h][q]);
+        oks[q] = j0 + q < M && pass_match<PASS>(keys[q], prefix) && keys[q] <= prune;
+        any_ok |= oks[q];
+      }
+      if (__ballot_sync(FULL, any_ok) == 0) continue;          // nobody in these 128 elements takes part
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t key = keys[q];
+        const bool ok = oks[q];
         const unsigned part = __ballot_sync(FULL, ok);
         if (part == 0) continue;
         const uint32_t d = ok ? pass_digit<PASS>(key) : 0x10000u;

@@ -119,3 +119,49 @@ def test_synth_shapes_are_seeded():
     e = a["train_edges"]
     assert e.shape == (1500, 2) and np.all(e[:, 0] < e[:, 1]) and e.max() < a["n"]
     assert np.unique(e[:, 0] * a["n"] + e[:, 1]).size == 1500
+
+
+@pytest.mark.parametrize("shape", ["tiny", "small"])
+def test_owner_bounds_and_slab_plan(shape):
+    """candidates.owner_bounds is an upper bound of every owner's candidate count (it sizes the padded slots
+    of the one-pass kernel) and filter_step.iter_slabs cuts the owners into consecutive ranges whose
+    capacities respect slab_pairs and add up to the bound of the whole range."""
+    from edge_proposal_sets_b200 import candidates, filter_step
+    from util import to_adj
+    s, ei, w, g = synth_graph(shape)
+    adj = to_adj(g, "cpu")
+    cand = og.two_hop_candidates(g)
+    counts = np.bincount(cand[1], minlength=g.n)
+    bounds = candidates.owner_bounds(adj).numpy()
+    assert bounds.shape == (g.n,) and np.all(bounds >= counts)
+    deg = np.diff(g.rowptr)
+    assert np.all(bounds <= np.maximum(g.n - 1 - deg, 0))
+    assert np.all(bounds[deg == 0] == 0)
+    for lo_hi in [(0, g.n), (g.n // 3, g.n // 2), (5, 5)]:
+        for slab_pairs in (1, 977, 50_000, 10**9):
+            plan = list(filter_step.iter_slabs(adj, lo_hi[0], lo_hi[1], slab_pairs))
+            if lo_hi[0] == lo_hi[1]:
+                assert plan == []
+                continue
+            assert plan[0][0] == lo_hi[0] and plan[-1][1] == lo_hi[1]
+            assert all(a[1] == b[0] for a, b in zip(plan, plan[1:]))           # consecutive, no gaps
+            assert sum(p[2] for p in plan) == int(bounds[lo_hi[0]:lo_hi[1]].sum())
+            for lo, hi, cap in plan:
+                assert cap == int(bounds[lo:hi].sum())
+                assert cap <= slab_pairs or hi - lo == 1                       # a hub gets a slab of its own
+                assert int(counts[lo:hi].sum()) <= cap
+
+
+def test_values_symmetric_detects_asymmetric_weights():
+    from edge_proposal_sets_b200 import candidates
+    from util import to_adj
+    s, ei, w, g = synth_graph("tiny")
+    assert candidates.values_symmetric(to_adj(g, "cpu"))                       # unweighted
+    key = np.minimum(np.repeat(np.arange(g.n), np.diff(g.rowptr)), g.col) * g.n + \
+        np.maximum(np.repeat(np.arange(g.n), np.diff(g.rowptr)), g.col)
+    uk, inv = np.unique(key, return_inverse=True)
+    g.val = (np.random.default_rng(1).random(uk.size).astype(np.float32) + 0.5)[inv]
+    assert candidates.values_symmetric(to_adj(g, "cpu", keep_values=True))
+    g.val = g.val.copy()
+    g.val[0] += 1.0
+    assert not candidates.values_symmetric(to_adj(g, "cpu", keep_values=True))
