@@ -38,15 +38,18 @@ namespace eps {
 constexpr int TS_THREADS = 512;
 constexpr int TS_LONG = 96;   // lists at least this long are streamed warp-wide without a search
 
-// Visit every element of the neighbour lists of N(v) (a warp takes 32 lists at a time).
+// Visit every element of the neighbour lists of N(v).  A warp takes LG lists at a time (LG = 32, 16, ... 1,
+// warp-uniform): the caller picks the largest LG that still gives every warp of the CTA a group, so an owner
+// of average degree (74 on the ppa shape) keeps all 16 warps busy instead of three — the kernel is
+// latency-bound, so idle warps are lost time.
 // f.visit(u, p) is called once per 2-path v - k - u (p = index of u in `col`, i.e. inside N(k)) after
 // f.select_slot*(lane that holds k's metadata).
 template <typename F>
 __device__ __forceinline__ void walk_two_paths(const int *__restrict__ rowptr, const int *__restrict__ col,
-                                               int vs, int ve, int warp, int nwarps, int lane, F f) {
-  for (int base = vs + warp * 32; base < ve; base += nwarps * 32) {
+                                               int vs, int ve, int warp, int nwarps, int lane, int LG, F f) {
+  for (int base = vs + warp * LG; base < ve; base += nwarps * LG) {
     int k = -1, s = 0, len = 0;
-    if (base + lane < ve) {
+    if (lane < LG && base + lane < ve) {
       k = __ldg(col + base + lane);
       s = __ldg(rowptr + k);
       len = __ldg(rowptr + k + 1) - s;
@@ -86,8 +89,7 @@ __device__ __forceinline__ void walk_two_paths(const int *__restrict__ rowptr, c
     for (int j = 0; j < total; j += 32) {
       const int p = j + lane;
       int lo = 0;
-#pragma unroll
-      for (int step = 16; step >= 1; step >>= 1) {
+      for (int step = LG >> 1; step >= 1; step >>= 1) {      // first slot whose inclusive prefix exceeds p
         int t = __shfl_sync(FULL, pin, lo + step - 1);
         if (t <= p) lo += step;
       }
@@ -183,10 +185,12 @@ twohop_score_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
     const int v = s_owner;
     if (v >= v_hi) break;
     const int vs = __ldg(rowptr + v), ve = __ldg(rowptr + v + 1);
+    int LG = 32;                                           // lists per warp group: every warp gets a group
+    while (LG > 1 && (ve - vs + LG - 1) / LG < NW) LG >>= 1;
     const long long out_base = offsets[v - v_lo];
     if (offsets[v - v_lo + 1] == out_base) continue;   // no (room for) candidates (uniform): bitmap untouched
     // ---- 1. mark ----
-    walk_two_paths(rowptr, col, vs, ve, warp, NW, lane, MarkVisitor{bm, bm2});
+    walk_two_paths(rowptr, col, vs, ve, warp, NW, lane, LG, MarkVisitor{bm, bm2});
     __syncthreads();
     // ---- 2. clear known edges and the diagonal ----
     for (int p = vs + tid; p < ve; p += TS_THREADS) {
@@ -273,7 +277,7 @@ twohop_score_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
       ScoreVisitor<HAS_W, WANT_CN, HAS_VAL> sv{bm, blk, pre, wtable, val,
                                                (HAS_W || HAS_VAL) ? acc + out_base : nullptr,
                                                WANT_CN ? cn + out_base : nullptr};
-      walk_two_paths(rowptr, col, vs, ve, warp, NW, lane, sv);
+      walk_two_paths(rowptr, col, vs, ve, warp, NW, lane, LG, sv);
     }
     __syncthreads();
     // ---- 5. cleanup ----

@@ -74,3 +74,29 @@ def test_rank_side_hits_match_oracle():
     for K in rank_step.HITS["fb"]:
         want = (orank.hits_at_k(ptr, nv, K), orank.hits_at_k(pv, nv, K), orank.hits_at_k(pt, nt, K))
         assert got[f"Hits@{K}"] == pytest.approx(want, abs=0)
+
+
+@pytest.mark.timeout(200)
+def test_email_shape_cn_filter_then_cn_rank(tmp_path):
+    """BASELINE configs[0]: Common Neighbours filter + CN rank on the email graph (here its seeded
+    synthetic shape: the bundled email-Eu-core file is one of the reference's missing blobs).  The saved
+    proposal list must be the oracle's stable sort of ALL 2-hop candidates, bit for bit."""
+    import argparse
+    from edge_proposal_sets_b200.data import get_data
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-u", os.path.join(ROOT, "filter.py"), "--dataset", "email-shape", "--model", "simple",
+                        "--checkpoint", "email-shape_simple||0|0.pt"], cwd=tmp_path, env=env, capture_output=True,
+                       text=True, timeout=150)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = torch.load(tmp_path / "filtered_edges" / "email-shape_simple__0_0_sorted_edges.pt").numpy()
+    torch.manual_seed(0)
+    edge_index, edge_weight, split_edge, data = get_data(argparse.Namespace(dataset="email-shape", use_feature=False), "cpu")
+    g = og.add_edges("email-shape", edge_index.numpy(), edge_weight.numpy(), np.zeros((2, 0), np.int64), data.num_nodes)
+    cand, cn = og.two_hop_candidates(g, return_values=True)
+    want = orank.sorted_edges(cand, cn.astype(np.float32))
+    assert got.shape == want.shape and np.array_equal(got, want)        # k = None keeps every candidate, like the reference
+    r2 = subprocess.run([sys.executable, "-u", os.path.join(ROOT, "rank.py"), "--dataset", "email-shape", "--model", "simple",
+                         "--sorted_edge_path", "email-shape_simple__0_0_sorted_edges.pt", "--num_sorted_edge", "1500",
+                         "--runs", "1"], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=150)
+    assert r2.returncode == 0, r2.stderr[-2000:]
+    assert "Using 1500 highest scoring edges" in r2.stdout and "Hits@20" in r2.stdout
