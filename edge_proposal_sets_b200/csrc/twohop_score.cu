@@ -35,7 +35,8 @@
 
 namespace eps {
 
-constexpr int TS_THREADS = 512;
+constexpr int TS_THREADS = 512;           // two-pass entry point
+constexpr int TS_DEFAULT_THREADS = 512;   // one-pass entry point (see eps_twohop_onepass)
 constexpr int TS_LONG = 96;   // lists at least this long are streamed warp-wide without a search
 
 // Visit every element of the neighbour lists of N(v).  A warp takes LG lists at a time (LG = 32, 16, ... 1,
@@ -158,8 +159,8 @@ struct ScoreVisitor {
   }
 };
 
-template <bool HAS_W, bool WANT_CN, bool ONEPASS, bool HAS_VAL = false>
-__global__ void __launch_bounds__(TS_THREADS)
+template <bool HAS_W, bool WANT_CN, bool ONEPASS, bool HAS_VAL = false, int THREADS = TS_THREADS>
+__global__ void __launch_bounds__(THREADS)
 twohop_score_kernel(const int *__restrict__ rowptr, const int *__restrict__ col, const float *__restrict__ val,
                     const float *__restrict__ wtable, int n, int v_lo, int v_hi,
                     const long long *__restrict__ offsets, int *__restrict__ pair_u,
@@ -173,11 +174,11 @@ twohop_score_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
   uint32_t *blk = bm2 + W2;          // #candidates before block g
   uint16_t *pre = reinterpret_cast<uint16_t *>(blk + W2);   // #candidates before word w inside its block
   __shared__ int s_owner;
-  __shared__ uint32_t s_scan[TS_THREADS / 32];
+  __shared__ uint32_t s_scan[THREADS / 32];
   __shared__ uint32_t s_carry;
   const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
-  constexpr int NW = TS_THREADS / 32;
-  for (int w = tid; w < W + W2; w += TS_THREADS) sm[w] = 0;
+  constexpr int NW = THREADS / 32;
+  for (int w = tid; w < W + W2; w += THREADS) sm[w] = 0;
   for (;;) {
     __syncthreads();
     if (tid == 0) s_owner = v_lo + (int)atomicAdd(owner_counter, 1u);
@@ -193,7 +194,7 @@ twohop_score_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
     walk_two_paths(rowptr, col, vs, ve, warp, NW, lane, LG, MarkVisitor{bm, bm2});
     __syncthreads();
     // ---- 2. clear known edges and the diagonal ----
-    for (int p = vs + tid; p < ve; p += TS_THREADS) {
+    for (int p = vs + tid; p < ve; p += THREADS) {
       const int k = __ldg(col + p);
       atomicAnd(&bm[k >> 5], ~(1u << (k & 31)));
     }
@@ -201,7 +202,7 @@ twohop_score_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
     if (tid == 0) s_carry = 0;
     __syncthreads();
     // ---- 3a. rank: thread t owns block c + t (32 bitmap words) ----
-    for (int c = 0; c < W2; c += TS_THREADS) {
+    for (int c = 0; c < W2; c += THREADS) {
       const int g = c + tid;
       const uint32_t m2 = (g < W2) ? bm2[g] : 0u;
       uint32_t cnt = 0;
@@ -242,7 +243,7 @@ twohop_score_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
       // padded slot: record the real count (a violated bound poisons N instead of overrunning the slot)
       if (tid == 0) counts_out[v - v_lo] = fits ? total : 0xffffffffu;
       if (!fits) {
-        for (int g = tid; g < W2; g += TS_THREADS) {
+        for (int g = tid; g < W2; g += THREADS) {
           uint32_t m = bm2[g];
           while (m) {
             const int b = __ffs(m) - 1;
@@ -255,7 +256,7 @@ twohop_score_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
       }
     }
     // ---- 3b. emit pair_u / pair_v in ascending u ----
-    for (int g = tid; g < W2; g += TS_THREADS) {
+    for (int g = tid; g < W2; g += THREADS) {
       uint32_t m = bm2[g];
       long long o = out_base + blk[g];
       while (m) {
@@ -281,7 +282,7 @@ twohop_score_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
     }
     __syncthreads();
     // ---- 5. cleanup ----
-    for (int c = 0; c < W2; c += TS_THREADS) {
+    for (int c = 0; c < W2; c += THREADS) {
       const int g = c + tid;
       if (g < W2) {
         uint32_t m = bm2[g];
@@ -519,17 +520,27 @@ extern "C" int eps_twohop_onepass(const int32_t *rowptr, const int32_t *col, con
   if (cn) EPS_CUDA(cudaMemsetAsync(cn, 0, (size_t)cap * 4, stream));
   void (*kern)(const int *, const int *, const float *, const float *, int, int, int, const long long *, int *,
                int *, unsigned long long *, int *, unsigned int *, unsigned int *);
-  if (!want_score) kern = twohop_score_kernel<false, false, true>;
-  else if (val && wtable) kern = cn ? twohop_score_kernel<true, true, true, true> : twohop_score_kernel<true, false, true, true>;
-  else if (val) kern = cn ? twohop_score_kernel<false, true, true, true> : twohop_score_kernel<false, false, true, true>;
-  else if (wtable) kern = cn ? twohop_score_kernel<true, true, true> : twohop_score_kernel<true, false, true>;
-  else kern = twohop_score_kernel<false, true, true>;
+  // CTA size.  Measured (gpurun_out/r31, fused phase per step): 1024 threads help only where the bitmap limits
+  // the kernel to 2 CTAs per SM (ppa 12.6 -> 11.6 ms) and hurt where 512-thread CTAs already fill the SM
+  // (collab 4.6 -> 7.7 ms; ddi 8.1 -> 8.2): 512 stays the default, EPS_TS_THREADS=1024 overrides (A/B runs)
+  int threads = TS_DEFAULT_THREADS;
+  if (const char *e = getenv("EPS_TS_THREADS")) threads = atoi(e) == 1024 ? 1024 : 512;
+#define EPS_TS_PICK(T)                                                                                                  \
+  do {                                                                                                                  \
+    if (!want_score) kern = twohop_score_kernel<false, false, true, false, T>;                                         \
+    else if (val && wtable) kern = cn ? twohop_score_kernel<true, true, true, true, T> : twohop_score_kernel<true, false, true, true, T>;   \
+    else if (val) kern = cn ? twohop_score_kernel<false, true, true, true, T> : twohop_score_kernel<false, false, true, true, T>;           \
+    else if (wtable) kern = cn ? twohop_score_kernel<true, true, true, false, T> : twohop_score_kernel<true, false, true, false, T>;        \
+    else kern = twohop_score_kernel<false, true, true, false, T>;                                                      \
+  } while (0)
+  if (threads == 1024) EPS_TS_PICK(1024); else EPS_TS_PICK(512);
+#undef EPS_TS_PICK
   EPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
-  EPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TS_THREADS, smem));
+  EPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
   if (occ < 1) occ = 1;
   const int grid = (int)std::min<long long>((long long)n_own, (long long)sms * occ);
-  kern<<<grid, TS_THREADS, smem, stream>>>(rowptr, col, val, wtable, n, v_lo, v_hi,
+  kern<<<grid, threads, smem, stream>>>(rowptr, col, val, wtable, n, v_lo, v_hi,
                                            (const long long *)bound_offsets, pad_u, nullptr, acc, cn,
                                            (unsigned int *)ws, counts);
   EPS_LAUNCH_CHECK();
