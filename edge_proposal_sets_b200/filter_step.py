@@ -11,10 +11,10 @@ B200-native restatement of the body of /root/reference/filter.py:92-166:
   all_scores[:,2].sort(descending=True)  # CPU      K4 radix-select + stable sort of k rows
   torch.save([N,3])                                 [k,3] float32 (k = N keeps the full list)
 
-Slabs: owners are cut into contiguous ranges holding at most ``slab_pairs`` candidates, each
-slab's top-k is merged into a running top-k by concatenation in slab order + K4 — positions in
-the concatenation preserve the global candidate order, so the result equals a single global
-stable sort.  Multi-GPU: each rank takes a contiguous owner range (parallel.partition_by_work)
+Slabs: owners are cut into contiguous ranges whose candidate BOUND is at most ``slab_pairs``
+(``iter_slabs``); every slab is folded into the running proposal set by one K4 selection over
+(running list ++ slab) (``RunningTopK``) — positions in that concatenation preserve the global
+candidate order, so the final stable sort equals a single global stable sort.  Multi-GPU: each rank takes a contiguous owner range (parallel.partition_by_work)
 and the per-rank lists are merged with one all-gather (parallel.merge_topk).
 """
 from __future__ import annotations
@@ -105,16 +105,6 @@ def iter_slabs(adj: SparseAdj, v_lo: int, v_hi: int, slab_pairs: int) -> Iterato
         yield v_lo + lo, v_lo + hi, end - base
         base = end
         lo = hi
-
-
-def _merge_running(running: Optional[torch.Tensor], top: torch.Tensor, k: int) -> torch.Tensor:
-    """Merge two SORTED [*,3] lists (the older one first) into the sorted top-k (used for lists that are
-    already final, e.g. per-GPU results); the slab loop uses ``RunningTopK`` instead."""
-    if running is None:
-        return top
-    cat = torch.cat([running, top], 0)
-    idx, _ = ops.topk(cat[:, 2].contiguous(), min(k, cat.shape[0]))
-    return cat[idx]
 
 
 class RunningTopK:

@@ -64,7 +64,7 @@ def test_train_step_gradients_match_fp64_autograd(model_name, weighted):
     o64 = ognn.linkpred_forward(h64, torch.cat([pos, neg], 1).numpy(), sd64, L, torch.float64)
     l64 = train_step.link_loss(o64[:400], o64[400:])
     l64.backward()
-    assert float(loss) == pytest.approx(float(l64), rel=2e-6)
+    assert float(loss.detach()) == pytest.approx(float(l64.detach()), rel=2e-6)
     for k, p in model.named_parameters():
         gw, gg = sd64[k].grad.numpy(), p.grad.double().cpu().numpy()
         scale = max(np.abs(gw).max(), 1e-12)
@@ -119,8 +119,12 @@ def test_submit_job_flow_train_filter_rank(tmp_path):
     sd = torch.load(ckpt)
     assert sd["gnn.convs.0.weight"].shape == (300, 300) and "linkpred.lins.2.bias" in sd
     assert "Epoch: 04" in r.stdout and "Highest Valid" in r.stdout and "All runs:" in r.stdout
-    losses = [float(l.split("Loss: ")[1].split(",")[0]) for l in r.stdout.splitlines() if "Hits@20" not in l and "Loss: " in l]
-    assert losses[-1] < losses[0], losses
+    by_epoch = {}
+    for line in r.stdout.splitlines():
+        if "Loss: " in line and "Epoch: " in line:
+            by_epoch[int(line.split("Epoch: ")[1].split(",")[0])] = float(line.split("Loss: ")[1].split(",")[0])
+    losses = [by_epoch[e] for e in sorted(by_epoch)]
+    assert len(losses) == 4 and min(losses[1:]) < losses[0], losses
     r = run(os.path.join(ROOT, "filter.py"), "--dataset", "email-shape", "--model", "gcn",
             "--checkpoint", "email-shape_gcn||0|0.pt")
     assert r.returncode == 0, r.stderr[-3000:]
