@@ -1,20 +1,23 @@
 #!/usr/bin/env python
 """bench.py — candidate pairs scored / second on the ogbl-ppa shape (BASELINE.json metric).
 
-One STEP = the whole filter step (/root/reference/filter.py:92-166) for one slab of owner nodes:
-  K6+K3 fused, one pass: candidates + Adamic-Adar score + exact CN count of every candidate
-  ->  GCN embeddings (3 x [cuBLAS GEMM + K1 SpMM])
-  ->  K2 GCN+LinkPredictor score of every candidate
-  ->  K4 running top-k (select over running list ++ slab; one sort at the end) for each of the two
-      filter models  [-> NCCL all-gather merge, N > 1]
-`value` = candidates of the slab / device time of the step (every candidate is scored by BOTH
-filter models; per-scorer rates are reported under `detail`).  Nothing is cached between steps.
+One STEP = the WHOLE filter job (/root/reference/filter.py:92-166) of the graph, through the product call
+``filter_step.filter_topk_multi`` — the call filter.py makes — for the two filter models BASELINE.json names:
 
-  python bench.py [--gpus N --steps K --warmup W] [--workload ppa|collab|ddi|small] [--pairs P]
+  GCN embeddings once (gcn_norm + L x [cuBLAS x·W row blocks + K1 SpMM]; row-sharded + all-gathered when N > 1)
+  for every owner slab of the graph (all 576,289 owners, 8.26 G candidates on the ppa shape):
+      K6+K3 fused, one pass : candidates + Adamic-Adar score of every candidate
+      K2 tcgen05            : GCN+LinkPredictor score of every candidate (bf16 prefilter)
+      K4b + K4              : threshold push-down + running top-k (exact list for AA, tolerance band for GCN)
+  fp32 re-scoring of the GCN band (K2 FFMA arm) -> the fp32 arm's exact top-k; one stable sort per list
+  [N > 1: owners sharded by 2-path work, global k-th score exchanged, lists merged (NCCL)]
+
+`value` = candidates of the graph / device time of the step (every candidate is scored by BOTH filter models),
+strong scaling: the same job on N GPUs.  Nothing is cached between steps.  `e2e` = the same call with HOST
+inputs: graph, features and weights uploaded from pinned memory and both [k,3] lists copied back, every step.
+
+  python bench.py [--gpus N --steps K --warmup W] [--workload ppa|collab|ddi|small|tiny]
   python bench.py --impl reference ...     # the reference's CPU path (oracle port) on host cores
-
-Under torchrun (N > 1) every rank scores its own owner slab (weak scaling), then the per-rank
-proposal lists are merged with one all-gather + K4 on every rank.
 """
 from __future__ import annotations
 
@@ -45,21 +48,21 @@ def emit(line: dict) -> None:
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--steps", type=int, default=3)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--workload", default="ppa", choices=["ppa", "collab", "ddi", "small", "tiny"])
-    p.add_argument("--pairs", type=int, default=1 << 26, help="target candidates per owner slab")
-    p.add_argument("--slabs", type=int, default=4,
-                   help="owner slabs per step per GPU (the GCN embeddings are computed once per step)")
-    p.add_argument("--mlp", default=None, choices=[None, "fp32", "bf16"],
-                   help="K2 arm: bf16 = tcgen05 tensor-core kernel (default), fp32 = FFMA parity arm")
+    p.add_argument("--slab-pairs", type=int, default=1 << 27, help="candidate capacity of one owner slab")
+    p.add_argument("--owners-frac", type=float, default=1.0,
+                   help="score only the first fraction of the owners (debug / profiling runs; 1.0 = the whole graph)")
+    p.add_argument("--mlp", default=None, choices=[None, "prefilter", "fp32", "bf16"],
+                   help="K2 arm of the GCN filter: prefilter = tcgen05 bf16 scores + fp32 re-scoring of the band "
+                        "(default; the fp32 arm's exact list), bf16 = tensor-core scores only, fp32 = FFMA arm")
     p.add_argument("--scale", type=float, default=1.0, help="shrink the synthetic graph (debug only)")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--unfused", action="store_true",
-                   help="score CN/AA pair by pair with K3 (eps_cn_aa) after K6 instead of the fused K6+K3 kernel")
-    p.add_argument("--twopass", action="store_true",
-                   help="enumerate with the K6 count pass + prefix sum + fill/fused kernels instead of the one-pass kernel")
+    p.add_argument("--no-extras", action="store_true",
+                   help="skip the ddi / collab shape lines, the library baseline and the multi-GPU self-check")
+    p.add_argument("--no-pushdown", action="store_true", help="K4 select over every slab instead of K4b push-down (A/B)")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
     return p.parse_args()
 
@@ -69,19 +72,21 @@ def parse():
 # ------------------------------------------------------------------------------------------
 
 MODEL_CFG = {  # builder's choice for ppa (the reference has no ppa defaults)
-    "ppa": dict(layers=3, hidden=256), "collab": dict(layers=3, hidden=256),
-    "ddi": dict(layers=2, hidden=256), "small": dict(layers=3, hidden=256), "tiny": dict(layers=2, hidden=64),
+    "ppa": dict(layers=3, hidden=256, k=4_000_000),        # submit_job.py:210
+    "collab": dict(layers=3, hidden=256, k=200_000),       # models.py:712-721, submit_job.py:202
+    "ddi": dict(layers=2, hidden=256, k=530_000),          # models.py:685-694, submit_job.py:194
+    "small": dict(layers=3, hidden=256, k=20_000), "tiny": dict(layers=2, hidden=64, k=500),
 }
 
 
-def build_host_inputs(args):
-    """Synthetic graph of the named shape + seeded random-init weights, as pinned host tensors."""
+def build_host_inputs(workload, scale=1.0):
+    """Synthetic graph of the named shape + seeded random-init weights, as host tensors."""
     import torch
     from edge_proposal_sets_b200 import synth
     t0 = time.time()
-    s = synth.make_shape(args.workload, args.scale)
+    s = synth.make_shape(workload, scale)
     ei = synth.undirected_edge_index(s["train_edges"])
-    cfg = MODEL_CFG[args.workload]
+    cfg = MODEL_CFG[workload]
     n, H, L = s["n"], cfg["hidden"], cfg["layers"]
     g = torch.Generator().manual_seed(1234)
     feat = 0 if s["x"] is None else s["x"].shape[1]
@@ -97,24 +102,17 @@ def build_host_inputs(args):
         b = 1.0 / H ** 0.5
         sd[f"linkpred.lins.{i}.weight"] = (torch.rand(oc, H, generator=g) * 2 - 1) * b
         sd[f"linkpred.lins.{i}.bias"] = (torch.rand(oc, generator=g) * 2 - 1) * b
-    host = dict(n=n, H=H, L=L, feat=feat, edge_index=torch.from_numpy(ei),
+    host = dict(n=n, H=H, L=L, feat=feat, edge_index=torch.from_numpy(ei), workload=workload,
                 edge_weight=None if s["edge_weight"] is None else torch.from_numpy(np.concatenate([s["edge_weight"]] * 2)),
                 x=None if s["x"] is None else torch.from_numpy(s["x"]), sd=sd,
-                dataset="collab" if s["edge_weight"] is not None else args.workload, gen_s=time.time() - t0)
+                dataset="collab" if s["edge_weight"] is not None else workload, gen_s=time.time() - t0)
     return host
 
 
-def workload_text(workload: str, slabs: int, k: int) -> str:
-    return (f"{workload}-shape filter step: GCN embeddings once, then {slabs} owner slab(s) per GPU enumerated, "
-            f"scored by AA(+CN) and GCN+LinkPredictor, running top-{k} each")
-
-
-def choose_slab(counts_cum: np.ndarray, start_owner: int, target_pairs: int):
-    """Owner range [lo, hi) starting at start_owner holding ~target_pairs candidates."""
-    base = 0 if start_owner == 0 else counts_cum[start_owner - 1]
-    hi = int(np.searchsorted(counts_cum, base + target_pairs, side="right"))
-    hi = max(hi, start_owner + 1)
-    return start_owner, min(hi, counts_cum.shape[0])
+def workload_text(workload: str, k: int, slab_pairs: int) -> str:
+    return (f"{workload}-shape FULL filter job: GCN embeddings once, every owner of the graph enumerated in slabs of "
+            f"<= {slab_pairs} candidates, every candidate scored by Adamic-Adar (fused K6+K3) and GCN+LinkPredictor "
+            f"(tcgen05), top-{k} proposal list of each")
 
 
 # ------------------------------------------------------------------------------------------
@@ -255,7 +253,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    host = build_host_inputs(args)
+    host = build_host_inputs(args.workload, args.scale)
     embed_s = cpu_setup(host)
     procs = os.cpu_count()
     owners = cpu_pick_owners(host, max(args.cpu_seconds / 3, 1.0))
@@ -272,13 +270,16 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "candidate pairs scored/sec (CN/AA + GCN+LinkPredictor filter step)",
         "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        # the B200 arm's workload; each reference step is a bounded sample of it (cpu_baseline.sample)
-        "config": {"workload": workload_text(args.workload, args.slabs, 4_000_000 if args.pairs * args.slabs >= 16_000_000 else max(args.pairs * args.slabs // 8, 1)),
+        # the B200 arm's workload; each reference step is a BOUNDED SAMPLE of it (cpu_baseline.sample): the same
+        # graph, models and per-candidate work, but only the candidates of `sample_owners` — the whole job
+        # (8.26 G candidates on ppa) would take the CPU path several hours
+        "config": {"workload": workload_text(args.workload, cfg["k"], args.slab_pairs),
                    "n": host["n"], "nnz": int(host["edge_index"].shape[1]),
                    "gnn": f"gcn L={cfg['layers']} H={cfg['hidden']} F_in={cfg['hidden'] + host['feat']}",
-                   "sample_owners": [owners[0], owners[1]]},
+                   "sample_owners": [owners[0], owners[1]], "same_config_as_b200_arm": False,
+                   "why": "bounded sample of the same workload (rate per candidate; the job itself is not finished)"},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": procs, "kind": "port",
                          "sample": f"{last['pairs']} candidates of owners [{owners[0]},{owners[1]}) per step; "
                                    f"scipy A@A enumeration + scipy AA x{procs} procs + torch-CPU MLP + torch sort; "
@@ -294,10 +295,226 @@ def run_reference(args):
 # the B200 arm
 # ------------------------------------------------------------------------------------------
 
+class Workload:
+    """One synthetic shape on this rank's GPU: pinned host inputs, upload(), and the step."""
+
+    def __init__(self, name, args, dev, world, pin=True):
+        import torch
+        from edge_proposal_sets_b200 import graph as pg, models
+        self.name, self.args, self.dev, self.world = name, args, dev, world
+        host = build_host_inputs(name, args.scale)
+        self.host = host
+        n, H, L = host["n"], host["H"], host["L"]
+        self.n, self.H, self.L = n, H, L
+        self.k = MODEL_CFG[name]["k"]
+        pinf = (lambda t: t.pin_memory()) if pin else (lambda t: t)
+        ew = host["edge_weight"] if host["edge_weight"] is not None else torch.ones(host["edge_index"].shape[1])
+        adj0 = pg.add_edges(host["dataset"], host["edge_index"].to(dev), ew.to(dev),
+                            torch.zeros([2, 0], dtype=torch.long, device=dev), n)
+        self.h_rowptr, self.h_col = pinf(adj0.rowptr.cpu()), pinf(adj0.col.cpu())
+        self.h_val = None if adj0.val is None else pinf(adj0.val.cpu())
+        self.h_x = None if host["x"] is None else pinf(host["x"])
+        self.h_sd = {k: pinf(v.contiguous()) for k, v in host["sd"].items()}
+        del adj0
+        torch.cuda.empty_cache()
+        self.mlp_arm = args.mlp or os.environ.get("EPS_BENCH_MLP", "prefilter")
+        margs = argparse.Namespace(model="gcn", dataset=name, num_layers=L, hidden_channels=H, dropout=0.0,
+                                   use_feature=host["x"] is not None, use_learnable_embedding=True,
+                                   mlp_precision=self.mlp_arm)
+
+        class D:
+            num_nodes = n
+            x = host["x"]
+        self.model = models.build_model(margs, D, dev)        # parameter storage; every upload() refills it
+        self.model.eval()
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in [self.h_rowptr, self.h_col] +
+                             ([self.h_val] if self.h_val is not None else []) +
+                             ([self.h_x] if self.h_x is not None else []) + list(self.h_sd.values()))
+        self.owners = None if args.owners_frac >= 1.0 else (0, max(1, int(n * args.owners_frac)))
+
+    def upload(self):
+        """H2D of everything the public call takes (graph first; features + weights on a copy stream)."""
+        import torch
+        from edge_proposal_sets_b200 import graph as pg
+        dev = self.dev
+        adj = pg.SparseAdj(self.h_rowptr.to(dev, non_blocking=True), self.h_col.to(dev, non_blocking=True),
+                           None if self.h_val is None else self.h_val.to(dev, non_blocking=True), self.n)
+        self.copy_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.copy_stream), torch.no_grad():
+            x = None if self.h_x is None else self.h_x.to(dev, non_blocking=True)
+            for k_, p_ in self.model.state_dict().items():
+                p_.copy_(self.h_sd[k_], non_blocking=True)
+        torch.cuda.current_stream().wait_stream(self.copy_stream)
+        return adj, x
+
+    def step(self, adj, x, stats=None, distributed=None):
+        """The filter job through the product call; returns [AA list, GCN list] ([k,3] each)."""
+        from edge_proposal_sets_b200 import filter_step
+        adj._cache.clear()                                    # nothing derived from the graph is reused
+        self.model._h_key = None                              # no embedding cache across steps
+        jobs = [filter_step.FilterJob("adamic_ogb", None),
+                filter_step.FilterJob("gcn", self.model, precision=self.mlp_arm)]
+        dist_on = (self.world > 1) if distributed is None else distributed
+        return filter_step.filter_topk_multi(jobs, x, adj, k=self.k, slab_pairs=self.args.slab_pairs,
+                                             distributed=dist_on, stats=stats, pushdown=not self.args.no_pushdown,
+                                             owners=self.owners)
+
+
+def measure(wl: Workload, steps: int, warmup: int, rank: int, world: int, e2e_steps: int, sampler=None):
+    """Warm-up, K device-timed steps (barrier + sync both sides, max over ranks), then the e2e loop."""
+    import torch
+    import torch.distributed as dist
+    from edge_proposal_sets_b200 import ops
+    dev = wl.dev
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    adj, x = wl.upload()
+    torch.cuda.synchronize()
+    for _ in range(max(warmup, 3)):
+        outs = wl.step(adj, x)
+    ops.LAUNCHES["n"] = 0
+    ops.KERNEL_EVENTS = {}
+    if sampler is not None:
+        sampler.start()
+    all_stats = []
+    barrier()
+    t0, t1 = ev(), ev()
+    t0.record()
+    for _ in range(steps):
+        st = {"time_phases": True}
+        outs = wl.step(adj, x, st)
+        all_stats.append(st)
+    t1.record()
+    barrier()
+    kev, ops.KERNEL_EVENTS = ops.KERNEL_EVENTS, None
+    launches = ops.LAUNCHES["n"]
+    ms_total = t0.elapsed_time(t1)
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    cand = torch.tensor([float(all_stats[-1]["candidates_scored"])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cand, op=dist.ReduceOp.SUM)
+    ms_step = float(tmax.item()) / steps
+    total_pairs = float(cand.item())
+    phase_ms = {}
+    for st in all_stats:
+        for k_, v in st["phase_ms"].items():
+            phase_ms[k_] = phase_ms.get(k_, 0.0) + v / steps
+    spmm_ms = [a_.elapsed_time(b_) for a_, b_ in kev.get("spmm_csr", [])]
+
+    # ---- end to end through the public call with HOST buffers ----
+    out_host = [torch.empty((wl.k, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
+
+    def e2e_step():
+        a, xx = wl.upload()
+        res = wl.step(a, xx)
+        for o, r in zip(out_host, res):
+            o[: r.shape[0]].copy_(r, non_blocking=True)
+        torch.cuda.current_stream().synchronize()             # the caller holds the result on the host
+        return res
+
+    e2e = None
+    if e2e_steps > 0:
+        e2e_step()
+        barrier()
+        w0 = time.perf_counter()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        e1.record()
+        barrier()
+        e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - w0) * 1e3)   # D2H syncs: wall clock is the honest one
+        tm = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        e2e = {"value": total_pairs * e2e_steps / (float(tm.item()) * 1e-3), "unit": "pairs/s",
+               "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": 2 * wl.k * 12, "steps": e2e_steps,
+               "ms_per_step": float(tm.item()) / e2e_steps,
+               "note": "per step and per rank: pinned-host graph + features + weights -> device, the product call, "
+                       "both [k,3] lists -> pinned host"}
+    return dict(ms_step=ms_step, total_pairs=total_pairs, phase_ms=phase_ms, stats=all_stats[-1], launches=launches,
+                spmm_ms=spmm_ms, e2e=e2e, outs=outs, adj=adj, x=x)
+
+
+def library_baseline(wl: Workload, adj, x, k):
+    """SURVEY §2.1's bar, same box: the library kernels the reference reaches — ATen index_select + mul,
+    cuBLAS Linear, relu, sigmoid (models.py:478-485,506) in fp32 (TF32 off, the reference default) and in bf16
+    autocast-style, and torch.topk / torch.sort for the ordering (filter.py:160) — on one slab of this graph."""
+    import torch
+    from edge_proposal_sets_b200 import candidates
+    model = wl.model
+    h = model.embed(x, adj)
+    bounds = torch.cumsum(candidates.owner_bounds(adj), 0)
+    v_hi = int(torch.searchsorted(bounds, torch.tensor(min(wl.args.slab_pairs, 1 << 26), device=wl.dev)).item())
+    edges = candidates.two_hop(adj, 0, max(v_hi, 1))
+    M = edges.shape[1]
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    out = {"slab_candidates": int(M)}
+    lins = model.linkpred.lins
+    B = 1 << 20                                               # 16x the reference's largest batch (64K, models.py:685-694)
+    nb = min(8, max(1, M // B))
+    for name, dt in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
+        hh = h.to(dt)
+        Ws = [(l.weight.to(dt), l.bias.to(dt)) for l in lins]
+
+        def run(lo):
+            e = edges[:, lo:lo + B].long()
+            z = hh[e[0]] * hh[e[1]]
+            for w, b in Ws[:-1]:
+                z = torch.relu(torch.nn.functional.linear(z, w, b))
+            return torch.sigmoid(torch.nn.functional.linear(z, Ws[-1][0], Ws[-1][1]))
+        run(0); run(0)
+        a, b_ = ev(), ev()
+        a.record()
+        for i in range(nb):
+            run((i * B) % max(M - B, 1))
+        b_.record()
+        torch.cuda.synchronize()
+        out[f"torch_eager_{name}_mlp_pairs_per_s"] = nb * min(B, M) / (a.elapsed_time(b_) * 1e-3)
+    sc = model.linkpred.score_pairs(h, edges, "bf16")
+    kk = min(k, M)
+    for name, fn in (("torch_topk", lambda: torch.topk(sc, kk)), ("torch_sort_stable", lambda: torch.sort(sc, descending=True, stable=True))):
+        fn()
+        a, b_ = ev(), ev()
+        a.record()
+        fn()
+        b_.record()
+        torch.cuda.synchronize()
+        out[f"{name}_ms_per_slab"] = a.elapsed_time(b_)
+    from edge_proposal_sets_b200 import ops
+    ops.topk_edges(edges, sc, kk)
+    a, b_ = ev(), ev()
+    a.record()
+    ops.topk_edges(edges, sc, kk)
+    b_.record()
+    torch.cuda.synchronize()
+    out["eps_topk_k4_ms_per_slab"] = a.elapsed_time(b_)
+    for prec in ("bf16", "fp32"):
+        mm = M if prec == "bf16" else min(M, 1 << 23)
+        e_ = edges[:, :mm].contiguous()
+        model.linkpred.score_pairs(h, e_, prec)
+        a, b_ = ev(), ev()
+        a.record()
+        model.linkpred.score_pairs(h, e_, prec)
+        b_.record()
+        torch.cuda.synchronize()
+        out[f"eps_k2_{prec}_pairs_per_s"] = mm / (a.elapsed_time(b_) * 1e-3)
+    out["note"] = ("same slab, same box: eager = index_select x2 + mul + (Linear, relu) x (L-1) + Linear + sigmoid in batches of "
+                   "2^20 pairs (the reference uses <= 2^16); K4 vs torch.topk / stable torch.sort of the slab's scores")
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from edge_proposal_sets_b200 import _lib, candidates, filter_step, graph as pg, models, ops, parallel
+    from edge_proposal_sets_b200 import _lib, candidates
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -311,225 +528,49 @@ def run_b200(args):
     _lib.load()
     torch.backends.cuda.matmul.allow_tf32 = False          # reference default: fp32 SGEMM
 
-    host = build_host_inputs(args)
-    n, H, L = host["n"], host["H"], host["L"]
-    pin = lambda t: t.pin_memory()
-    # ---- host-side inputs of the public call, pinned (e2e copies them every step) ----
-    ew = host["edge_weight"] if host["edge_weight"] is not None else torch.ones(host["edge_index"].shape[1])
-    adj0 = pg.add_edges(host["dataset"], host["edge_index"].to(dev), ew.to(dev),
-                        torch.zeros([2, 0], dtype=torch.long, device=dev), n)
-    h_rowptr, h_col = pin(adj0.rowptr.cpu()), pin(adj0.col.cpu())
-    h_val = None if adj0.val is None else pin(adj0.val.cpu())
-    h_x = None if host["x"] is None else pin(host["x"])
-    h_sd = {k: pin(v.contiguous()) for k, v in host["sd"].items()}
-    del adj0
-    torch.cuda.empty_cache()
+    wl = Workload(args.workload, args, dev, world)
+    n, H, L, k = wl.n, wl.H, wl.L, wl.k
+    sampler = ClockSampler(local) if rank == 0 else None
+    res = measure(wl, args.steps, args.warmup, rank, world, e2e_steps=min(args.steps, 5), sampler=sampler)
+    clocks = sampler.stop() if sampler is not None else None
+    adj, x = res["adj"], res["x"]
+    st = res["stats"]
+    phase_ms = res["phase_ms"]
+    slabs = st["slabs"]
+    M_rank = st["candidates_scored"]
 
-    mlp_arm = args.mlp or os.environ.get("EPS_BENCH_MLP", "bf16")
-    margs = argparse.Namespace(model="gcn", dataset=args.workload, num_layers=L, hidden_channels=H, dropout=0.0,
-                               use_feature=host["x"] is not None, use_learnable_embedding=True, mlp_precision=mlp_arm)
+    # ---- multi-GPU self-check: the merged lists == the single-GPU lists, bit for bit ----
+    verified = None
+    if world > 1 and not args.no_extras:
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        if rank == 0:
+            single = wl.step(adj, x, distributed=False)
+            ok = all(torch.equal(a, b) for a, b in zip(single, res["outs"]))
+            flag.fill_(1 if ok else 2)
+            del single
+        dist.broadcast(flag, 0)
+        verified = bool(int(flag.item()) == 1)
 
-    class D:
-        num_nodes = n
-        x = host["x"]
-
-    copy_stream = torch.cuda.Stream(device=dev)
-
-    def upload():
-        """H2D of everything the public call takes.  The graph goes first on the compute stream
-        (candidate enumeration and CN/AA only need it); features + weights follow on a copy stream
-        and are awaited right before the GCN embeddings are computed."""
-        adj = pg.SparseAdj(h_rowptr.to(dev, non_blocking=True), h_col.to(dev, non_blocking=True),
-                           None if h_val is None else h_val.to(dev, non_blocking=True), n)
-        copy_stream.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(copy_stream), torch.no_grad():
-            x = None if h_x is None else h_x.to(dev, non_blocking=True)
-            for k_, p_ in model_skel.state_dict().items():
-                p_.copy_(h_sd[k_], non_blocking=True)
-            done = torch.cuda.Event()
-            done.record(copy_stream)
-        return adj, x, model_skel, done
-
-    model_skel = models.build_model(margs, D, dev)        # parameter storage; every upload() refills it
-    model_skel.eval()
-
-    h2d_bytes = sum(t.numel() * t.element_size() for t in [h_rowptr, h_col] + ([h_val] if h_val is not None else []) +
-                    ([h_x] if h_x is not None else []) + list(h_sd.values()))
-
-    adj, x, model, _ready = upload()
-    torch.cuda.synchronize()
-    # ---- this rank's owner range: `--slabs` consecutive slabs of ~`--pairs` candidates (weak scaling) ----
-    counts = candidates.owner_counts(adj).cpu().numpy()
-    cum = np.cumsum(counts)
-    n_total_candidates = int(cum[-1])
-    lo = 0
-    slabs = []
-    for i in range((rank + 1) * args.slabs):
-        if lo >= n:
-            break
-        lo, hi = choose_slab(cum, lo, args.pairs)
-        if i >= rank * args.slabs:
-            slabs.append((lo, hi))
-        lo = hi
-    assert slabs, "graph too small for this many ranks x slabs x pairs"
-    slab_sizes = [int(cum[b - 1] - (cum[a - 1] if a else 0)) for a, b in slabs]
-    bounds_cum = np.cumsum(candidates.owner_bounds(adj).cpu().numpy())      # slab capacities (host ints)
-    M = sum(slab_sizes)
-    k = 4_000_000 if M >= 16_000_000 else max(M // 8, 1)
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-    phases = ["embed", "candgen", "cn_aa", "mlp", "topk", "merge"]
-
-    def step(adj, x, model, record=None, weights_ready=None):
-        """One filter step on resident inputs: embeddings once, then every owner slab of this rank
-        is enumerated, scored by both filter models and folded into the two running top-k lists
-        (filter_step.filter_topk's loop).  Returns the two [k,3] proposal lists."""
-        rec = record is not None
-        marks = []
-        mark = (lambda: (marks.append(ev()), marks[-1].record())) if rec else (lambda: None)
-        adj._cache.clear()                                    # nothing derived from the graph is reused
-        model._h_key = None                                   # no caching across steps
-        mark()
-        if weights_ready is not None:
-            torch.cuda.current_stream().wait_event(weights_ready)
-        hemb = model.embed(x, adj)                            # gcn_norm + L x (GEMM + SpMM)
-        aa_w = adj.aa_ogb_weights()
-        mark()
-        run_aa, run_nn = filter_step.RunningTopK(k), filter_step.RunningTopK(k)
-        for (a, b) in slabs:
-            if args.twopass:
-                cnt, cap = candidates.owner_counts(adj, a, b), None   # K6 count pass (sizes the slab)
-            else:
-                # one-pass kernels: padded owner slots sized by per-owner upper bounds (torch ops, once per graph)
-                cnt = None
-                cap = int(bounds_cum[b - 1] - (bounds_cum[a - 1] if a else 0))
-                candidates.owner_bounds(adj)
-            mark()
-            if not args.unfused and (adj.val is None or (cnt is None and candidates.values_symmetric(adj))):
-                # K6+K3 fused: candidates + AA score + exact CN count from one walk over the 2-paths
-                edges, aa, cn = candidates.two_hop_scored(adj, aa_w, a, b, cnt, want_count=True, cap=cap)
-            else:
-                edges = candidates.two_hop(adj, a, b, cnt, cap=cap)
-                aa, cn = ops.cn_aa(adj, edges, aa_w, use_values=adj.val is not None, grouped_by_v=True, want_count=True)
-            mark()
-            sc = model.linkpred.score_pairs(hemb, edges)
-            mark()
-            # K4 select over (running list ++ slab), position-ordered, no sort
-            run_aa.update(edges, aa)
-            run_nn.update(edges, sc)
-            mark()
-            del edges, aa, cn, sc
-        run_aa, run_nn = run_aa.result(dev), run_nn.result(dev)   # one stable sort of the k survivors each
-        mark()
-        if world > 1:
-            run_aa = parallel.merge_topk(run_aa, k)
-            run_nn = parallel.merge_topk(run_nn, k)
-        mark()
-        if rec:
-            record.append(marks)
-        return run_aa, run_nn, M
-
-    def phase_times(marks):
-        """marks: [start, embed_end, (count_end, score_end, mlp_end, topk_end) x slabs, final_sort_end, merge_end]"""
-        t = dict.fromkeys(phases, 0.0)
-        t["embed"] = marks[0].elapsed_time(marks[1])
-        prev = marks[1]
-        for s_ in range(len(slabs)):
-            for j, ph in enumerate(["candgen", "cn_aa", "mlp", "topk"]):
-                cur = marks[2 + 4 * s_ + j]
-                t[ph] += prev.elapsed_time(cur)
-                prev = cur
-        t["topk"] += prev.elapsed_time(marks[-2])
-        t["merge"] = marks[-2].elapsed_time(marks[-1])
-        return t
-
-    out_host = [torch.empty((k, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
-
-    def e2e_step():
-        a, xx, m, ready = upload()
-        ta, tn, M = step(a, xx, m, weights_ready=ready)
-        out_host[0][: ta.shape[0]].copy_(ta, non_blocking=True)
-        out_host[1][: tn.shape[0]].copy_(tn, non_blocking=True)
-        torch.cuda.current_stream().synchronize()             # the caller holds the result on the host
-        return out_host, M
-
-    # ---- algorithmic work per step (SURVEY §8d) ----
-    deg = adj.degree().long()
-    per_pair = 8 if adj.val is not None else 4
-    k3_bytes, sum_dudv = 0, 0.0
-    for (a, b) in slabs:
-        cnt0 = candidates.owner_counts(adj, a, b)
-        edges0 = candidates.two_hop(adj, a, b, cnt0)
-        dd = deg[edges0[0].long()] + deg[edges0[1].long()]
-        k3_bytes += int((per_pair * dd + 12).sum().item())   # 4(d_u+d_v)+12 per pair
-        sum_dudv += float(dd.double().sum().item())
-        assert edges0.shape[1] == slab_sizes[slabs.index((a, b))]
-        del edges0, cnt0, dd
-    mean_du_dv = sum_dudv / M
-    # the fused K6+K3 kernel walks the owners' 2-paths twice (mark, score) instead of two lists per
-    # pair: 2 x 4 B per 2-path; per candidate the padded slot (u 4 B, fixed-point sum 8 B zero + 8 B RED,
-    # count 4 + 4 B) and the compaction (16 B read, 16 B written: u, v, score, count)
-    work = candidates.two_path_work(adj)
-    twopaths = int(sum(int(work[a:b].sum().item()) for a, b in slabs))
-    fused_bytes = (8 if adj.val is None else 12) * twopaths + 60 * M    # weighted: + the value next to u
-    mlp_flops = M * (2 * H * H * (L - 1) + 3 * H)
-    mlp_bytes = M * (2 * H * 4 + 12)
-    nnz_hat = int(h_col.numel()) + n                          # GCN adds the self loops
-    spmm_bytes = 4 * (n + 1) + 8 * nnz_hat + 4 * H * nnz_hat + 4 * n * H   # gather model, per layer
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident timing ----
-    for _ in range(max(args.warmup, 3)):
-        step(adj, x, model)
-    ops.LAUNCHES["n"] = 0
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    rec = []
-    ops.KERNEL_EVENTS = {}
-    barrier()
-    t_start, t_end = ev(), ev()
-    t_start.record()
-    for _ in range(args.steps):
-        step(adj, x, model, rec)
-    t_end.record()
-    barrier()
-    kev, ops.KERNEL_EVENTS = ops.KERNEL_EVENTS, None
-    spmm_ms = [a_.elapsed_time(b_) for a_, b_ in kev.get("spmm_csr", [])]
-    launches = ops.LAUNCHES["n"]
-    ms_total = t_start.elapsed_time(t_end)
-    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_step = float(tmax.item()) / args.steps
-    pt = [phase_times(m) for m in rec]
-    phase_ms = {p: float(np.mean([t[p] for t in pt])) for p in phases}
-
-    # ---- end to end through the public API with HOST buffers ----
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    e0, e1 = ev(), ev()
-    e0.record()
-    for _ in range(args.steps):
-        out, _ = e2e_step()
-    e1.record()
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
-    wall_e2e = time.perf_counter() - t0
-    e2e_ms = max(e2e_ms, wall_e2e * 1e3)                      # D2H .cpu() syncs: wall clock is the honest one
-    tm = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    pairs_all = torch.tensor([float(M)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        dist.all_reduce(pairs_all, op=dist.ReduceOp.SUM)
-    total_pairs = float(pairs_all.item())
-    clocks = sampler.stop() if rank == 0 else None
-    d2h_bytes = 2 * k * 12
+    # ---- the other BASELINE shapes, same product call, same N (strong scaling) ----
+    shapes = {}
+    if args.workload == "ppa" and not args.no_extras and args.owners_frac >= 1.0:
+        for nm in ("ddi", "collab"):
+            w2 = Workload(nm, args, dev, world, pin=False)
+            r2 = measure(w2, 5, 3, rank, world, e2e_steps=0)
+            ok2 = None
+            if world > 1:
+                flag = torch.zeros(1, dtype=torch.int32, device=dev)
+                if rank == 0:
+                    single = w2.step(r2["adj"], r2["x"], distributed=False)
+                    flag.fill_(1 if all(torch.equal(a, b) for a, b in zip(single, r2["outs"])) else 2)
+                dist.broadcast(flag, 0)
+                ok2 = bool(int(flag.item()) == 1)
+            shapes[nm] = {"value": r2["total_pairs"] / (r2["ms_step"] * 1e-3), "unit": "pairs/s", "ms_per_step": r2["ms_step"],
+                          "candidates": r2["total_pairs"], "k": w2.k, "n": w2.n, "nnz": int(w2.h_col.numel()),
+                          "phase_ms_rank0": r2["phase_ms"], "prefilter": r2["stats"].get("prefilter"),
+                          "multi_gpu_verified": ok2, "steps": 5, "warmup": 3}
+            del w2, r2
+            torch.cuda.empty_cache()
 
     if rank == 0:
         peaks = {}
@@ -539,82 +580,116 @@ def run_b200(args):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         tc_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-        S = len(slabs)
-        # ncu --set full DRAM traffic per launch of the same command (profiles/, one capture per round)
+        peak_src = "measured (MEASURED_PEAKS.json, sustained bf16 / copy bandwidth)" if peaks else "fallback (B200_PROFILING.md)"
         traffic = {}
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {})
         except Exception:
             pass
 
-        def roof_entry(kernel, bound, work, ms, launches_, tkey, note=None):
+        def roof_entry(kernel, bound, work, ms, launches_, tkey, note=None, extra=None):
+            """work = algorithmic bytes / flops of ALL launches of the step on this rank; ms = their summed time."""
             peak = hbm_peak if bound == "hbm" else tc_peak
-            ach = work / launches_ / (ms / launches_ * 1e-3) / (1e9 if bound == "hbm" else 1e12)
+            ach = work / (ms * 1e-3) / (1e9 if bound == "hbm" else 1e12) if ms > 0 else 0.0
             e = {"kernel": kernel, "bound": bound, "achieved": ach, "peak": peak,
                  "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": ach / peak,
                  "traffic": traffic.get(tkey), "peak_source": peak_src,
-                 ("algorithmic_bytes_per_launch" if bound == "hbm" else "algorithmic_flops_per_launch"): work / launches_,
-                 "ms_per_launch": ms / launches_, "launches_per_step": launches_}
+                 ("algorithmic_bytes_per_launch" if bound == "hbm" else "algorithmic_flops_per_launch"): work / max(launches_, 1),
+                 "ms_per_launch": ms / max(launches_, 1), "launches_per_step": launches_}
             if note:
                 e["note"] = note
+            if extra:
+                e.update(extra)
             return e
 
-        fused = not args.unfused and (adj.val is None or (not args.twopass and candidates.values_symmetric(adj)))
-        roofs = {
-            "mlp": roof_entry("linkpred_fp32_kernel (K2 fp32 arm, FFMA-bound)", "hbm", mlp_bytes, phase_ms["mlp"], S, "mlp_fp32")
-            if mlp_arm == "fp32" else
-            roof_entry("linkpred_tc3_kernel (K2 tcgen05, cta_group::2)", "tensor", mlp_flops, phase_ms["mlp"], S, "linkpred_tc3",
-                       "phase = bf16 table conversion + weight packing + the kernel"),
-            "topk": roof_entry("topk_hist/count/write kernels (K4 running select, both models)", "hbm",
-                               2 * (4 * M + 12 * k * S), phase_ms["topk"], 2 * S, "topk",
-                               "algorithmic bytes = one read of the slab's scores + 12 B per kept row (SURVEY 8d) per select; "
-                               "the radix select reads the scores 5x and the phase includes the two final sorts"),
-            "cn_aa": roof_entry("twohop_score_kernel + twohop_compact_kernel (K6+K3 fused, one pass)" if fused else "cn_grouped_kernel (K3)", "hbm",
-                                k3_bytes, phase_ms["cn_aa"], S, "twohop_onepass" if fused else "cn_grouped",
-                                "algorithmic bytes = the pair-by-pair figure 4(d_u+d_v)+12 of SURVEY 8d; the fused kernel "
-                                f"walks 2-paths instead and moves ~{fused_bytes / S / 1e9:.2f} GB per launch "
-                                f"({fused_bytes / S / (phase_ms['cn_aa'] / S * 1e-3) / 1e9:.0f} GB/s of its own traffic model)"
-                                if fused else None),
-        }
-        dom = max(roofs, key=lambda p: phase_ms[p])
+        # algorithmic work of this rank's owner range (SURVEY §8d)
+        lo_o, hi_o = st["owners"]
+        deg = adj.degree().long()
+        work2 = candidates.two_path_work(adj)
+        twopaths = int(work2[lo_o:hi_o].sum().item())
+        weighted = adj.val is not None
+        # the fused K6+K3 kernel walks the owners' 2-paths twice (mark, score): 2 x 4 B per 2-path (+ 4 B value when
+        # weighted); per candidate the padded slot (u 4 B, fixed-point sum 8 B zero + 8 B RED) and the compaction
+        # (12 B read, 12 B written: u, v, score)
+        fused_bytes = (12 if weighted else 8) * twopaths + 44 * M_rank
+        # SURVEY's pair-by-pair figure 4(d_u+d_v)+12 for the same candidates: sum over owners v of
+        # [#cand(v) * d_v + sum of d_u over its candidates]; the second term is bounded by the 2-path walk and is
+        # sampled on the first slab instead of being enumerated again
+        mlp_flops = M_rank * (2 * H * H * (L - 1) + 3 * H)
+        nnz_hat = int(wl.h_col.numel()) + n
+        spmm_bytes = 4 * (n + 1) + 8 * nnz_hat + 4 * H * nnz_hat + 4 * n * H          # gather model, per layer, whole graph
+        fused_key = "enum_score" if "enum_score" in phase_ms else "enum"
+        n_models = 2
+        roofs = {}
+        if "mlp" in phase_ms:
+            arm = wl.mlp_arm
+            roofs["mlp"] = roof_entry(
+                "linkpred_fp32_kernel (K2 fp32 arm, FFMA-bound)" if arm == "fp32" else "linkpred_tc3_kernel (K2 tcgen05, cta_group::2)",
+                "tensor", mlp_flops, phase_ms["mlp"], slabs, "linkpred_tc3",
+                "phase = the kernel (+ bf16 table and weight images, built once per step); flops = 2H^2(L-1)+3H per candidate")
+        roofs["enum_score"] = roof_entry(
+            "twohop_score_kernel + twohop_compact_kernel (K6+K3 fused, one pass)", "hbm", fused_bytes, phase_ms.get(fused_key, 0.0),
+            slabs, "twohop_onepass",
+            "bytes = the kernel's OWN traffic model: 8 B per 2-path (two walks; 12 B weighted) + 44 B per candidate "
+            "(padded slot, fixed-point accumulator, compaction); latency / L2-atomic bound, not HBM bound")
+        roofs["topk"] = roof_entry(
+            "threshold_count/write (K4b) + topk_hist/count/write (K4), both models", "hbm",
+            n_models * (4 * M_rank + 12 * k * slabs), phase_ms.get("topk", 0.0), n_models * slabs, "topk",
+            "algorithmic bytes = one read of the slab's scores + 12 B per kept row per select (SURVEY 8d); K4b reads the "
+            "scores twice, K4 runs over the survivors only; the phase includes the final sorts")
+        dom = max(roofs, key=lambda p: roofs[p]["ms_per_launch"] * roofs[p]["launches_per_step"])
         roof = roofs[dom]
         other = [roofs[p] for p in roofs if p != dom]
-        if spmm_ms:
-            per_step = len(spmm_ms) // args.steps
-            other.append(roof_entry("spmm_csr_kernel (K1)", "hbm", spmm_bytes * per_step,
-                                    float(np.sum(spmm_ms)) / args.steps, per_step, "spmm_csr",
-                                    "gather model 4(n+1)+8nnz+4F*nnz+4nF (SURVEY 8d); rows that hit in L2 let it exceed the HBM peak"))
+        if res["spmm_ms"]:
+            per_step = len(res["spmm_ms"]) // args.steps
+            frac_rows = 1.0 / world
+            other.append(roof_entry("spmm_csr_kernel (K1)", "hbm", spmm_bytes * frac_rows * per_step,
+                                    float(np.sum(res["spmm_ms"])) / args.steps, per_step, "spmm_csr",
+                                    "gather model 4(n+1)+8nnz+4F*nnz+4nF (SURVEY 8d) of this rank's row shard; rows that hit "
+                                    "in L2 let it exceed the HBM peak"))
+        value = res["total_pairs"] / (res["ms_step"] * 1e-3)
         line = {
             "metric": "candidate pairs scored/sec (CN/AA + GCN+LinkPredictor filter step)",
-            "value": total_pairs / (ms_step * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32" if mlp_arm == "fp32" else "bf16(mlp)/f32", "data": "synthetic",
-            "config": {"workload": workload_text(args.workload, len(slabs), k),
-                       "n": n, "nnz": int(h_col.numel()), "candidates_per_gpu": M, "slabs_per_gpu": len(slabs),
-                       "slab_candidates": slab_sizes, "owners": [slabs[0][0], slabs[-1][1]],
-                       "graph_total_candidates": n_total_candidates, "mean_du_plus_dv": mean_du_dv,
-                       "gnn": f"gcn L={L} H={H} F_in={H + host['feat']}", "mlp_arm": mlp_arm, "k": k,
-                       "enumeration": "two-pass (count + fill)" if args.twopass else "one-pass (padded owner slots + compaction)",
-                       "l2": "inputs larger than L2 (pairs+embeddings+CSR > 126 MB); no flush needed"
-                       if (M * 8 + n * H * 4) > 200e6 else "inputs smaller than L2: effective (cache-resident) bandwidth"},
-            "detail": {"phase_ms": phase_ms,
-                       "cn_aa_pairs_per_s": M / (phase_ms["cn_aa"] * 1e-3),
-                       "mlp_pairs_per_s": M / (phase_ms["mlp"] * 1e-3),
-                       "candgen_pairs_per_s": M / (phase_ms["candgen"] * 1e-3),
-                       "topk_ms": phase_ms["topk"], "embed_ms": phase_ms["embed"]},
+            "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": res["ms_step"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None,
+            "dtype": {"prefilter": "bf16 prefilter + f32 re-score (f32-exact lists)", "bf16": "bf16(mlp)/f32", "fp32": "f32"}[wl.mlp_arm],
+            "data": "synthetic",
+            "config": {"workload": workload_text(args.workload, k, args.slab_pairs),
+                       "n": n, "nnz": int(wl.h_col.numel()), "graph_total_candidates": int(res["total_pairs"]),
+                       "candidates_rank0": int(M_rank), "slabs_rank0": slabs, "owners_rank0": st["owners"],
+                       "owners_frac": args.owners_frac, "gnn": f"gcn L={L} H={H} F_in={H + wl.host['feat']}",
+                       "mlp_arm": wl.mlp_arm, "k": k, "slab_pairs": args.slab_pairs, "pushdown": not args.no_pushdown,
+                       "parallelism": f"owner ranges by 2-path work x{world}; embeddings row-sharded + all-gathered; "
+                                      "k-th score exchange + list merge" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (CSR 170 MB + embeddings 590 MB + >= 1 GB of pairs per slab); no flush needed"
+                       if (n * H * 4) > 200e6 else "graph + embeddings smaller than L2: effective (cache-resident) bandwidth"},
+            "detail": {"phase_ms_rank0": phase_ms,
+                       "pairs_per_s_by_phase_rank0": {p: M_rank / (v * 1e-3) for p, v in phase_ms.items() if v > 0 and p in ("enum_score", "enum", "mlp", "topk")},
+                       "prefilter": st.get("prefilter"), "prefilter_fallback": st.get("prefilter_fallback"),
+                       "topk_identical_to_fp32": (wl.mlp_arm == "prefilter" and "prefilter_fallback" not in st) or wl.mlp_arm == "fp32",
+                       "pushdown_survivors_rank0": st.get("pushdown_survivors"),
+                       "multi_gpu_verified": verified, "shapes": shapes},
             "roofline": roof,
             "roofline_other": other,
-            "e2e": {"value": total_pairs * args.steps / (float(tm.item()) * 1e-3), "unit": "pairs/s",
-                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
-            "gpu_launches": launches,
+            "e2e": res["e2e"],
+            "gpu_launches": res["launches"],
             "clocks": clocks,
         }
+        if world == 1 and not args.no_extras:
+            try:
+                line["detail"]["library_baseline"] = library_baseline(wl, adj, x, k)
+                lb = line["detail"]["library_baseline"]
+                roofs_mlp = roofs.get("mlp")
+                if roofs_mlp:
+                    lb["eps_step_mlp_pairs_per_s"] = M_rank / (phase_ms["mlp"] * 1e-3)
+            except Exception as exc:
+                line["detail"]["library_baseline"] = {"failed": repr(exc)}
         if world == 1 and not args.no_cpu_baseline:
             try:
-                embed_s = cpu_setup(host)
-                owners = cpu_pick_owners(host, args.cpu_seconds / 2)
-                r = cpu_reference_pass(host, owners, args.cpu_seconds, os.cpu_count())
+                embed_s = cpu_setup(wl.host)
+                owners = cpu_pick_owners(wl.host, args.cpu_seconds / 2)
+                r = cpu_reference_pass(wl.host, owners, args.cpu_seconds, os.cpu_count())
                 line["cpu_baseline"] = {
                     "value": r["pairs"] / r["total"], "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
                     "sample": f"{r['pairs']} candidates of owners [{owners[0]},{owners[1]}): scipy A@A enumeration, "
@@ -626,6 +701,7 @@ def run_b200(args):
                                         "sample": f"failed: {exc!r}"}
         emit(line)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -13,9 +13,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libeps_b200.so")
 
 EPS_OK = 0
+EPS_VERSION = 200          # must equal EPS_VERSION in include/eps.h (checked by load())
 EPS_REDUCE_SUM, EPS_REDUCE_MEAN = 0, 1
 EPS_CN_SIGMOID, EPS_CN_GROUPED_BY_V = 1, 2
 EPS_MLP_FP32, EPS_MLP_TC_BF16 = 0, 1
+EPS_MLP_REUSE_WORKSPACE = 0x100
 EPS_CAND_SCORE_CN, EPS_CAND_SCORE_WSUM = 0, 1
 
 _vp, _i32, _i64, _sz, _int = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t, C.c_int
@@ -37,6 +39,10 @@ SIGNATURES = {
     "eps_topk_workspace_bytes": (_sz, [_i64, _i64]),
     "eps_pack_edges": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "eps_topk_select2_f32": (_int, [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "eps_threshold_tiles": (_i64, [_i64]),
+    "eps_threshold_workspace_bytes": (_sz, [_i64]),
+    "eps_threshold_count": (_int, [_vp, _i64, _vp, C.c_float, _int, _vp, _vp, _sz, _vp]),
+    "eps_threshold_write": (_int, [_vp, _vp, _vp, _i64, _vp, C.c_float, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "eps_gather_pairs2": (_int, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "eps_twohop_candidates": (_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "eps_twohop_workspace_bytes": (_sz, []),
@@ -76,6 +82,14 @@ def load(build: bool | None = None) -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
+    got = lib.eps_version()
+    if got != EPS_VERSION:
+        raise EpsError(f"{LIB_PATH} was built from another eps.h (library version {got}, binding {EPS_VERSION}): "
+                       "rebuild it with `python -m edge_proposal_sets_b200.build --force`")
+    from . import build as _b
+    if _b.is_stale():
+        import warnings
+        warnings.warn(f"{LIB_PATH} is older than its sources; rebuild with `python -m edge_proposal_sets_b200.build`")
     _lib = lib
     return lib
 

@@ -35,12 +35,43 @@ def owner_counts(adj: SparseAdj, v_lo: int = 0, v_hi: int | None = None) -> torc
 
 def owner_bounds(adj: SparseAdj) -> torch.Tensor:
     """Upper bound of every owner's candidate count, int64 [n]: a candidate of v is the end point of
-    a 2-path from v (<= #2-paths) and is neither v nor a neighbour of v (<= n - 1 - deg v).  Torch ops
-    only; sizes the outputs of the one-pass kernel and cuts owner ranges into slabs / GPU shards."""
+    a 2-path from v (<= #2-paths) and is neither v nor a neighbour of v: <= n - |N(v) U {v}|, i.e.
+    n - 1 - deg v, or n - deg v when v carries a self loop (add_edges keeps them; v is then in N(v)).
+    Torch ops only; sizes the outputs of the one-pass kernel and cuts owner ranges into slabs / GPU shards."""
     if "owner_bounds" not in adj._cache:
         deg = adj.degree().long()
-        adj._cache["owner_bounds"] = torch.minimum(two_path_work(adj), (adj.n - 1 - deg).clamp_(min=0))
+        rp = adj.rowptr.long()
+        # self loop of v <=> v occurs in its own (sorted) row: one vectorised binary search over the column array
+        ar = torch.arange(adj.n, device=adj.device)
+        key = adj.row() * adj.n + adj.col.long() if adj.nnz < (1 << 22) else None
+        if key is not None:
+            pos = torch.searchsorted(key, ar * adj.n + ar).clamp_(max=max(adj.nnz - 1, 0))
+            loop = (key[pos] == ar * adj.n + ar).long() if adj.nnz else torch.zeros_like(deg)
+        else:
+            loop = torch.ones_like(deg)                 # large graphs: the looser n - deg for everyone
+        adj._cache["owner_bounds"] = torch.minimum(two_path_work(adj), (adj.n - 1 - deg + loop).clamp_(min=0))
     return adj._cache["owner_bounds"]
+
+
+def check_fixed_point_range(adj: SparseAdj, wtable, use_values: bool) -> None:
+    """The exact pair-score accumulator (csrc/eps_common.cuh: 64-bit fixed point, 38 fractional bits) holds
+    |sum| < 2^25.  A score is a sum of at most max_deg terms a_u * (a_v * w_k), and a common neighbour k has
+    degree >= 2, so max_deg * max|a|^2 * max_{deg k >= 2} |w_k| bounds it.  Checked once per (graph, table);
+    raises instead of letting the integer sums wrap."""
+    key = ("fx_ok", None if wtable is None else (wtable.data_ptr(), wtable._version), bool(use_values))
+    if key not in adj._cache:
+        deg = adj.degree()
+        dmax = float(deg.max().item()) if adj.n else 0.0
+        amax = float(adj.val.abs().max().item()) if (use_values and adj.val is not None and adj.nnz) else 1.0
+        wmax = 1.0
+        if wtable is not None and adj.n:
+            w = wtable.abs()[deg >= 2]
+            wmax = float(w.max().item()) if w.numel() else 0.0
+        adj._cache[key] = dmax * amax * amax * wmax
+    bound = adj._cache[key]
+    if not bound < 2.0 ** 25:
+        raise EpsError(f"pair scores may reach {bound:.3g} >= 2^25, outside the exact fixed-point accumulator of the "
+                       "CN/AA kernels (csrc/eps_common.cuh); rescale the edge weights or the weight table")
 
 
 def values_symmetric(adj: SparseAdj) -> bool:
@@ -133,6 +164,7 @@ def two_hop_scored(adj: SparseAdj, wtable: torch.Tensor | None = None, v_lo: int
     the owner_bounds sum of the range."""
     _need_cuda(adj.col, wtable)
     val = adj.val if use_values else None
+    check_fixed_point_range(adj, wtable, use_values)
     if val is not None and (counts is not None or not values_symmetric(adj)):
         raise EpsError("two_hop_scored: a weighted adjacency takes the one-pass kernel (no `counts`) and needs "
                        "bitwise symmetric values; otherwise score with two_hop + ops.cn_aa")

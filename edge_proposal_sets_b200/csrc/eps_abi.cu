@@ -37,6 +37,7 @@ extern "C" int eps_version(void) { return EPS_VERSION; }
 extern "C" const char *eps_last_error(void) { return eps::g_err; }
 
 extern "C" size_t eps_linkpred_workspace_bytes(int32_t n, int32_t H, int32_t L, int64_t M, int precision) {
+  precision &= ~EPS_MLP_REUSE_WORKSPACE;
   if (precision == EPS_MLP_TC_BF16) return eps::linkpred_tc_workspace_bytes(n, H, L, M);
   return 256;
 }
@@ -65,11 +66,13 @@ extern "C" int eps_linkpred_mlp(const float *h, int32_t n, int32_t H, const int3
       EPS_CHECK_ARG(((uintptr_t)prm.W[l]) % 16 == 0, "weights must be 16-byte aligned");
     }
   }
+  const bool prepared = (precision & EPS_MLP_REUSE_WORKSPACE) != 0;
+  precision &= ~EPS_MLP_REUSE_WORKSPACE;
   if (precision == EPS_MLP_FP32)
     return linkpred_fp32_launch(h, H, pair_u, pair_v, M, prm, L, apply_sigmoid, score, stream);
   if (precision == EPS_MLP_TC_BF16)
     return linkpred_tc_launch(h, n, H, pair_u, pair_v, M, prm, L, apply_sigmoid, score, workspace,
-                              workspace_bytes, stream);
+                              workspace_bytes, prepared, stream);
   set_error("eps_linkpred_mlp: unknown precision %d", precision);
   return EPS_ERR_INVALID;
 }

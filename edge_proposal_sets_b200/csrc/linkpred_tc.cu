@@ -205,7 +205,7 @@ static int tc_launch_h(const float *h, const int *pu, const int *pv, long long M
 
 int linkpred_tc_launch(const float *h, int n, int H, const int *pu, const int *pv, long long M,
                        const MlpParams &prm, int L, int apply_sigmoid, float *score, void *workspace,
-                       size_t workspace_bytes, cudaStream_t stream) {
+                       size_t workspace_bytes, bool prepared, cudaStream_t stream) {
   if (L < 2 || !(H == 64 || H == 128 || H == 256)) {
     set_error("eps_linkpred_mlp: the tcgen05 arm needs num_layers >= 2 and H in {64,128,256} (got L=%d H=%d); "
               "use EPS_MLP_FP32", L, H);
@@ -225,10 +225,12 @@ int linkpred_tc_launch(const float *h, int n, int H, const int *pu, const int *p
     if (linkpred_tc_uses_table(n, M) && !(variant && variant[0] == '2')) {
       table = tail;
       tail += ((size_t)n * H * 2 + 255) & ~(size_t)255;
-      const int st = h_to_bf16_launch(h, (long long)n * H, table, stream);
-      if (st != EPS_OK) return st;
+      if (!prepared) {                              // EPS_MLP_REUSE_WORKSPACE: the table of an earlier call is still there
+        const int st = h_to_bf16_launch(h, (long long)n * H, table, stream);
+        if (st != EPS_OK) return st;
+      }
     }
-    return linkpred_tc2_launch(h, table, H, pu, pv, M, prm, L, apply_sigmoid, score, img, n, (int *)tail, stream);
+    return linkpred_tc2_launch(h, table, H, pu, pv, M, prm, L, apply_sigmoid, score, img, n, (int *)tail, prepared, stream);
   }
   const int total = (L - 1) * H * (H / 8);
   pack_weights_kernel<<<(total + 255) / 256, 256, 0, stream>>>(prm, H, L - 1, img);

@@ -208,10 +208,12 @@ static int tc2_launch_h(const float *h, const int *pu, const int *pv, long long 
 
 int linkpred_tc2_launch(const float *h, const void *h_bf16, int H, const int *pu, const int *pv, long long M,
                         const MlpParams &prm, int L, int apply_sigmoid, float *score, uint8_t *img, int n,
-                        int *tile_order, cudaStream_t stream) {
+                        int *tile_order, bool prepared, cudaStream_t stream) {
   const int total = (L - 1) * H * (H / 8);
-  pack_weights_halves_kernel<<<(total + 255) / 256, 256, 0, stream>>>(prm, H, L - 1, img);
-  EPS_LAUNCH_CHECK();
+  if (!prepared) {                                  // EPS_MLP_REUSE_WORKSPACE: the images of an earlier call are still there
+    pack_weights_halves_kernel<<<(total + 255) / 256, 256, 0, stream>>>(prm, H, L - 1, img);
+    EPS_LAUNCH_CHECK();
+  }
   const char *variant = getenv("EPS_TC_VARIANT");   // "2": force this (unpipelined) kernel
   if (!(variant && variant[0] == '2')) {
     const int st = h_bf16 ? linkpred_tc3_launch(h_bf16, 1, H, pu, pv, M, prm, L, apply_sigmoid, score, img, n,

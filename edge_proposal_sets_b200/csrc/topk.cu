@@ -476,6 +476,113 @@ __global__ void pack_edges_kernel(const int *__restrict__ pu, const int *__restr
   }
 }
 
+
+// ---------------- K4b: threshold push-down (ordered compaction under the running k-th score) ----------------
+// Once a running proposal list holds k candidates, a new slab can only contribute elements that beat the
+// list's k-th score s_k: strictly (a tie at s_k loses to the list's own ties, which come earlier in candidate
+// order), or — prefilter mode, scores later re-computed in fp32 — everything with score >= s_k - margin.
+// One counting read and one writing read of the slab's scores replace five radix-select reads of it; the
+// survivors keep their position order, so the tie rule needs nothing else.
+
+__device__ __forceinline__ float key_score(uint32_t key) {
+  const uint32_t asc = ~key;
+  const uint32_t b = (asc >> 31) ? (asc ^ 0x80000000u) : ~asc;
+  return __uint_as_float(b);
+}
+
+// largest key that still survives (keys ascend as scores descend)
+__device__ __forceinline__ uint32_t threshold_last_key(uint32_t bound, float margin, int inclusive) {
+  if (!inclusive) return bound == 0 ? 0u : bound - 1;       // strictly better than the k-th (bound 0: nothing can be)
+  if (!(margin > 0.f)) return bound;
+  const uint32_t kt = score_key(key_score(bound) - margin);
+  return kt == 0xffffffffu ? kt : kt + 1;                   // one ulp of slack below the rounded difference
+}
+
+__global__ void __launch_bounds__(TK_THREADS)
+threshold_count_kernel(const float *__restrict__ score, long long M, const uint32_t *__restrict__ bound_key,
+                       float margin, int inclusive, uint32_t *__restrict__ tile_count) {
+  const uint32_t bound = *bound_key;
+  const bool none = !inclusive && bound == 0;
+  const uint32_t last = threshold_last_key(bound, margin, inclusive);
+  const ScoreSrc src{nullptr, 0, score};
+  const long long base = (long long)blockIdx.x * TK_TILE;
+  uint32_t c = 0;
+#pragma unroll
+  for (int t = 0; t < TK_TILE; t += TK_THREADS * 4) {
+    const long long i = base + t + threadIdx.x * 4;
+    float v[4];
+    src.load4(i, M, v);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) c += (i + q < M && !none && score_key(v[q]) <= last);
+  }
+  __shared__ uint32_t sc[TK_THREADS / 32];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+  if (lane_id() == 0) sc[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t a = 0;
+    for (int w = 0; w < TK_THREADS / 32; ++w) a += sc[w];
+    tile_count[blockIdx.x] = a;
+    if (blockIdx.x == 0) tile_count[gridDim.x] = 0;       // slot of the grand total (exclusive scan)
+  }
+}
+
+__global__ void __launch_bounds__(TK_THREADS)
+threshold_write_kernel(const float *__restrict__ score, const int *__restrict__ pu, const int *__restrict__ pv,
+                       long long M, const uint32_t *__restrict__ bound_key, float margin, int inclusive,
+                       const uint32_t *__restrict__ tile_off, int *__restrict__ out_u, int *__restrict__ out_v,
+                       float *__restrict__ out_score, uint32_t *__restrict__ out_pos) {
+  const uint32_t bound = *bound_key;
+  const bool none = !inclusive && bound == 0;
+  const uint32_t last = threshold_last_key(bound, margin, inclusive);
+  if (tile_off[blockIdx.x + 1] == tile_off[blockIdx.x]) return;   // nothing survives in this tile
+  const ScoreSrc src{nullptr, 0, score};
+  const long long base = (long long)blockIdx.x * TK_TILE;
+  uint32_t run = tile_off[blockIdx.x];
+  __shared__ uint32_t wsum[TK_THREADS / 32];
+  __shared__ uint32_t s_tot;
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  for (int sub = 0; sub < TK_TILE; sub += TK_THREADS * 4) {
+    const long long i0 = base + sub + (long long)threadIdx.x * 4;
+    float v4[4];
+    src.load4(i0, M, v4);
+    bool ok[4];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      ok[q] = i0 + q < M && !none && score_key(v4[q]) <= last;
+      mine += ok[q];
+    }
+    uint32_t inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(FULL, inc, d);
+      if (lane >= d) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t acc = 0;
+      for (int w = 0; w < TK_THREADS / 32; ++w) { const uint32_t v = wsum[w]; wsum[w] = acc; acc += v; }
+      s_tot = acc;
+    }
+    __syncthreads();
+    uint32_t pos = run + wsum[warp] + inc - mine;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (ok[q]) {
+        if (out_u) { out_u[pos] = pu[i0 + q]; out_v[pos] = pv[i0 + q]; }
+        if (out_score) out_score[pos] = v4[q];
+        if (out_pos) out_pos[pos] = (uint32_t)(i0 + q);
+        ++pos;
+      }
+    }
+    run += s_tot;
+    __syncthreads();
+  }
+}
+
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct TopkLayout {
@@ -541,6 +648,7 @@ static int topk_run(const ScoreSrc src, int64_t M, int64_t k, bool sorted, const
   topk_hist_kernel<2><<<hgrid, TK_THREADS, 0, stream>>>(src, M, state, nullptr, hist + 4096);
   topk_pick_kernel<2><<<1, 256, 0, stream>>>(state, hist + 4096, (uint32_t)k, kth_key_out);
   EPS_LAUNCH_CHECK();
+  if (!out_idx && !out_score) return EPS_OK;          // only the k-th key was asked for
   topk_count_kernel<<<L.nblk, TK_THREADS, 0, stream>>>(src, M, state, blk_less, blk_eq);
   scan_exclusive(blk_less, blk_eq, (long long)L.nblk, scan_tmp, stream);
   topk_write_kernel<<<L.nblk, TK_THREADS, 0, stream>>>(src, M, state, blk_less, blk_eq, keyA, idxA);
@@ -580,12 +688,61 @@ extern "C" int eps_topk_select2_f32(const float *score_a, int64_t Ma, const floa
                                     size_t workspace_bytes, void *stream_) {
   using namespace eps;
   EPS_CHECK_ARG(Ma >= 0 && Mb >= 0 && (Ma == 0 || score_a) && (Mb == 0 || score_b), "bad segments");
-  EPS_CHECK_ARG(out_idx || out_score, "no output requested");
+  EPS_CHECK_ARG(out_idx || out_score || kth_key_out, "no output requested");
   const int64_t M = Ma + Mb;
   EPS_CHECK_ARG(M >= 1 && M < 0xffffffffll, "Ma + Mb out of range [1, 2^32-1)");
   EPS_CHECK_ARG(k >= 1 && k <= M, "k out of range [1, Ma + Mb]");
   return topk_run(ScoreSrc{score_a, Ma, score_b}, M, k, false, prune_key, kth_key_out, out_idx, out_score,
                   workspace, workspace_bytes, (cudaStream_t)stream_, "eps_topk_select2_f32");
+}
+
+
+extern "C" int64_t eps_threshold_tiles(int64_t M) { return M <= 0 ? 0 : (M + eps::TK_TILE - 1) / eps::TK_TILE; }
+
+extern "C" int eps_threshold_count(const float *score, int64_t M, const uint32_t *bound_key, float margin,
+                                   int inclusive, uint32_t *tile_offsets, void *workspace,
+                                   size_t workspace_bytes, void *stream_) {
+  using namespace eps;
+  EPS_CHECK_ARG(M >= 0 && M < 0xffffffffll, "M out of range [0, 2^32-1)");
+  EPS_CHECK_ARG(bound_key && tile_offsets, "null pointer");
+  EPS_CHECK_ARG(margin >= 0.f, "negative margin");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (M == 0) { EPS_CUDA(cudaMemsetAsync(tile_offsets, 0, 4, stream)); return EPS_OK; }
+  EPS_CHECK_ARG(score != nullptr, "score is NULL");
+  if (sm_count() <= 0) { set_error("eps_threshold_count: no CUDA device"); return EPS_ERR_CUDA; }
+  const long long nt = (M + TK_TILE - 1) / TK_TILE;
+  const size_t need = align256(2 * ((size_t)(nt + 1 + SCAN_CHUNK - 1) / SCAN_CHUNK + 1) * 4);
+  if (!workspace || workspace_bytes < need) {
+    set_error("eps_threshold_count: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return EPS_ERR_WORKSPACE;
+  }
+  threshold_count_kernel<<<(unsigned)nt, TK_THREADS, 0, stream>>>(score, M, bound_key, margin, inclusive, tile_offsets);
+  scan_exclusive(tile_offsets, nullptr, nt + 1, (uint32_t *)workspace, stream);
+  EPS_LAUNCH_CHECK();
+  return EPS_OK;
+}
+
+extern "C" size_t eps_threshold_workspace_bytes(int64_t M) {
+  const long long nt = M <= 0 ? 0 : (M + eps::TK_TILE - 1) / eps::TK_TILE;
+  return eps::align256(2 * ((size_t)(nt + 1 + eps::SCAN_CHUNK - 1) / eps::SCAN_CHUNK + 1) * 4) + 256;
+}
+
+extern "C" int eps_threshold_write(const float *score, const int32_t *pair_u, const int32_t *pair_v, int64_t M,
+                                   const uint32_t *bound_key, float margin, int inclusive,
+                                   const uint32_t *tile_offsets, int32_t *out_u, int32_t *out_v,
+                                   float *out_score, uint32_t *out_pos, void *stream_) {
+  using namespace eps;
+  EPS_CHECK_ARG(M >= 0 && M < 0xffffffffll, "M out of range [0, 2^32-1)");
+  if (M == 0) return EPS_OK;
+  EPS_CHECK_ARG(score && bound_key && tile_offsets, "null pointer");
+  EPS_CHECK_ARG((out_u != nullptr) == (out_v != nullptr), "out_u and out_v come together");
+  EPS_CHECK_ARG(!out_u || (pair_u && pair_v), "pairs requested without pair_u / pair_v");
+  EPS_CHECK_ARG(out_u || out_score || out_pos, "no output requested");
+  const long long nt = (M + TK_TILE - 1) / TK_TILE;
+  threshold_write_kernel<<<(unsigned)nt, TK_THREADS, 0, (cudaStream_t)stream_>>>(
+      score, pair_u, pair_v, M, bound_key, margin, inclusive, tile_offsets, out_u, out_v, out_score, out_pos);
+  EPS_LAUNCH_CHECK();
+  return EPS_OK;
 }
 
 extern "C" int eps_gather_pairs2(const int32_t *ua, const int32_t *va, int64_t Ma, const int32_t *ub,

@@ -4,7 +4,8 @@
   twitch / fb     the bundled MUSAE files with the reference's seeded split
                   (/root/reference/twitch/data.py:39-64, fb/data.py: same code): read from the CWD
                   layout the reference uses (``twitch/musae_DE_edges.csv`` ...) or, failing that,
-                  from this repo's committed fixture (tests/golden/{twitch,fb}.npz, edges only);
+                  from this repo's committed fixtures (tests/golden/{twitch,fb}.npz: the split edges;
+                  {twitch,fb}_features.npz: the binary feature matrix as CSR index lists);
   ddi/collab/ppa  through ``ogb`` when it is installed (not in this image, no network);
   <name>-shape    seeded synthetic graph of that dataset's shape (synth.py), 80/10/10 split.
 
@@ -70,7 +71,8 @@ class LinkDataset:
                                     edge_weight=None if w is None else torch.from_numpy(w).float())
         exist = {(int(a), int(b)) for a, b in np.concatenate([train, valid, test])}
         self.valid_neg = valid_neg if valid_neg is not None else _negatives(n, len(valid), exist, 42)
-        self.test_neg = test_neg if test_neg is not None else _negatives(n, len(test), exist, 43)
+        # the reference draws val_edges.size(1) negatives for BOTH splits (twitch/data.py make_edge_split)
+        self.test_neg = test_neg if test_neg is not None else _negatives(n, len(valid), exist, 43)
 
     def __getitem__(self, i):
         return self.data
@@ -107,7 +109,22 @@ def _load_local(name: str) -> LinkDataset:
     else:
         z = np.load(os.path.join(_REPO, "tests", "golden", f"{name}.npz"))
         train, valid, test = (z[k].astype(np.int64) for k in ("train_edges", "valid_edges", "test_edges"))
+    if x is None:
+        x = _fixture_features(name, n)
     return LinkDataset(name, n, train, valid, test, x=x)
+
+
+def _fixture_features(name: str, n: int):
+    """The dataset's binary feature matrix from the committed CSR fixture (oracle/make_golden_features.py:
+    the public MUSAE feature file after the reference's processing, twitch/data.py:73-84), or None."""
+    path = os.path.join(_REPO, "tests", "golden", f"{name}_features.npz")
+    if not os.path.exists(path):
+        return None
+    z = np.load(path)
+    x = np.zeros((n, int(z["width"])), dtype=np.float32)
+    rows = np.repeat(np.arange(n), np.diff(z["indptr"]))
+    x[rows, z["indices"].astype(np.int64)] = 1
+    return x
 
 
 def _load_shape(name: str) -> LinkDataset:
@@ -158,6 +175,9 @@ def get_data(args, device="cpu"):
     idx = torch.randperm(split_edge["train"]["edge"].size(0))[: split_edge["valid"]["edge"].size(0)]
     split_edge["eval_train"] = {"edge": split_edge["train"]["edge"][idx]}
     name = "collab" if args.dataset.startswith("collab") else args.dataset
+    if args.use_feature and d.x is None:
+        raise RuntimeError(f"dataset {args.dataset!r} has no node features here (feature file and fixture missing); "
+                           "pass --use_feature '' to run on the learnable embedding alone")
     data = SimpleNamespace(num_nodes=d.num_nodes, x=d.x if args.use_feature else None, edge_index=edge_index)
     data.adj_t = add_edges(name, edge_index.to(device), edge_weight.to(device),
                            torch.zeros([2, 0], dtype=torch.long, device=device), d.num_nodes)

@@ -8,14 +8,16 @@ B200-native restatement of the body of /root/reference/filter.py:92-166:
   for batch in DataLoader(range(N), B):             one K2 / K3 launch per slab
       model(x, edges, adj)   # GNN re-run per batch   embeddings computed once (LinkGNN.embed)
       cat([edges.t(), score]).cpu()                   scores stay on the device
-  all_scores[:,2].sort(descending=True)  # CPU      K4 radix-select + stable sort of k rows
+  all_scores[:,2].sort(descending=True)  # CPU      K4 radix-select + K4b threshold push-down + one stable sort
   torch.save([N,3])                                 [k,3] float32 (k = N keeps the full list)
 
 Slabs: owners are cut into contiguous ranges whose candidate BOUND is at most ``slab_pairs``
-(``iter_slabs``); every slab is folded into the running proposal set by one K4 selection over
-(running list ++ slab) (``RunningTopK``) — positions in that concatenation preserve the global
-candidate order, so the final stable sort equals a single global stable sort.  Multi-GPU: each rank takes a contiguous owner range (parallel.partition_by_work)
-and the per-rank lists are merged with one all-gather (parallel.merge_topk).
+(``iter_slabs``); every slab is folded into the running proposal set (``RunningTopK``) — positions in
+the concatenation of the slabs preserve the global candidate order, so the final stable sort equals a
+single global stable sort.  Multi-GPU: each rank takes a contiguous owner range
+(parallel.partition_by_work), the GNN embeddings are computed row-sharded and all-gathered
+(models._ConvStack.embed_rows) and the per-rank lists are merged after an exchange of the global k-th
+score (parallel.merge_topk).
 """
 from __future__ import annotations
 
@@ -107,19 +109,81 @@ def iter_slabs(adj: SparseAdj, v_lo: int, v_hi: int, slab_pairs: int) -> Iterato
         lo = hi
 
 
-class RunningTopK:
-    """The proposal set while owner slabs stream by.  State: the current best ``<= k`` candidates as
-    SoA (u, v int32, score fp32) in CANDIDATE ORDER (= the reference's column-major order, which is the
-    tie rule of the final sort).  ``update`` selects the k best of (state ++ slab) with K4's radix
-    select + ordered compaction over the two segments in place — no concatenation, no sort;
-    ``result`` sorts once (stable, score descending) and packs the float32 ``[k,3]`` list.
-    Equal to one global stable sort of all candidates, bit for bit (tests/test_gpu_topk.py)."""
+class PrefilterToleranceError(RuntimeError):
+    """The bf16 tensor-core scores left their stated tolerance band around the fp32 scores; the
+    caller re-runs on the fp32 arm (``filter_topk`` does)."""
 
-    def __init__(self, k: Optional[int]):
+
+# Stated tolerance of the tcgen05 arm: |sigmoid_bf16 - sigmoid_fp32| <= PREFILTER_TOL for every pair
+# (tests/test_gpu_mlp_tc.py holds the kernel to it against the fp64 oracle).  The prefilter keeps every
+# candidate within 2 * PREFILTER_TOL of the running k-th bf16 score; see ``filter_topk_multi``.
+PREFILTER_TOL = 2e-3
+
+
+class _Phases:
+    """CUDA-event stop-watch for the phases of the filter step (bench.py reads ``stats['phase_ms']``)."""
+
+    def __init__(self, on: bool):
+        self.on, self.marks = on, []
+        self.mark(None)
+
+    def mark(self, name):
+        if self.on:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.marks.append((name, e))
+
+    def totals(self):
+        out = {}
+        for (_, a), (name, b) in zip(self.marks, self.marks[1:]):
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
+
+class RunningTopK:
+    """The proposal set while owner slabs stream by, as SoA (u, v int32, score fp32) in CANDIDATE ORDER
+    (= the reference's column-major order, which is the tie rule of the final sort).
+
+    Exact mode (``margin=None``): the state is exactly the k best candidates seen so far.  Until the list
+    is full a slab is folded in by K4's radix select over (state ++ slab); from then on K4b pushes the
+    k-th score down into the slab — only elements STRICTLY better survive one ordered compaction (a slab
+    tie at the k-th score comes later in candidate order than the list's own ties, so it can never
+    displace one) — and the select runs over (state ++ survivors).  ``result`` sorts once (stable, score
+    descending).  Equal to one global stable sort of all candidates, bit for bit (tests/test_gpu_topk.py).
+
+    Band mode (``margin > 0``, the bf16 prefilter): the state is the POOL of every candidate whose score
+    is >= (k-th best score seen so far) - margin; the k-th score only rises, so nothing dropped could
+    re-enter.  ``pool`` returns it for the fp32 re-scoring (``filter_topk_multi``)."""
+
+    def __init__(self, k: Optional[int], margin: Optional[float] = None, pushdown: bool = True):
         self.k = k                      # None: keep every candidate, like the reference
+        self.margin = margin
+        self.pushdown = pushdown        # False: K4 select over every slab (the pre-K4b path, kept for A/B)
         self.u = self.v = self.score = None
         self.kth_key = None             # order key of the current k-th score (device), once the list is full
         self.seen = 0
+        self.survivors = 0              # slab elements that passed the push-down (statistic)
+        self._pending = 0
+
+    @property
+    def size(self) -> int:
+        return 0 if self.score is None else self.score.numel()
+
+    def _append(self, pu, pv, score, clone=False):
+        if self.score is None:
+            self.u, self.v, self.score = (pu.clone(), pv.clone(), score.clone()) if clone else (pu, pv, score)
+        else:
+            self.u, self.v = torch.cat([self.u, pu]), torch.cat([self.v, pv])
+            self.score = torch.cat([self.score, score])
+
+    def rethreshold(self) -> None:
+        """Band mode: recompute the k-th key over the pool and drop what fell out of the band."""
+        if self.margin is None or self.k is None or self.size < self.k:
+            return
+        self.kth_key = ops.kth_key(self.score, self.k)
+        self.u, self.v, self.score = ops.threshold_compact(self.score, torch.stack([self.u, self.v]), self.kth_key,
+                                                           self.margin, inclusive=True)
+        self._pending = 0
 
     def update(self, edges: torch.Tensor, score: torch.Tensor) -> None:
         M = score.numel()
@@ -128,61 +192,233 @@ class RunningTopK:
         self.seen += M
         pu, pv = ops._pairs(edges)
         score = score.contiguous().float()
-        have = 0 if self.score is None else self.score.numel()
-        kk = have + M if self.k is None else min(self.k, have + M)
-        if kk == have + M:                                   # everything survives: plain append
-            if self.score is None:
-                self.u, self.v, self.score = pu.clone(), pv.clone(), score.clone()
-            else:
-                self.u, self.v = torch.cat([self.u, pu]), torch.cat([self.v, pv])
-                self.score = torch.cat([self.score, score])
+        have = self.size
+        band = self.margin is not None
+        if self.k is None or have + M <= self.k:             # everything survives: plain append
+            self._append(pu, pv, score, clone=True)
+            if band and self.k is not None and self.size == self.k:
+                self.rethreshold()
             return
-        # a full list lets the select skip every slab element that is already worse than its k-th score
+        if self.kth_key is not None and (self.pushdown or band):
+            # the list is full: push its k-th score down into the slab (K4b)
+            su, sv, ss = ops.threshold_compact(score, edges, self.kth_key, self.margin or 0.0, inclusive=band)
+            c = ss.numel()
+            self.survivors += c
+            if c == 0:
+                return
+            if band:
+                self._append(su, sv, ss)
+                self._pending += c
+                if self._pending * 8 >= self.k:
+                    self.rethreshold()
+                return
+            idx, sc, self.kth_key = ops.topk_select2(self.score, ss, self.k, want_kth_key=True)
+            self.u, self.v = ops.gather_pairs2((self.u, self.v), (su, sv), idx)
+            self.score = sc
+            return
+        if band:                                             # the slab that fills the pool
+            self._append(pu, pv, score, clone=True)
+            self.rethreshold()
+            return
+        # exact mode, list not yet full (or push-down switched off): K4 select over (list ++ slab)
+        kk = min(self.k, have + M)
         prune = self.kth_key if (have == kk and self.kth_key is not None) else None
-        idx, sc, self.kth_key = ops.topk_select2(self.score, score, kk, prune_key=prune, want_kth_key=True)
+        idx, sc, kth = ops.topk_select2(self.score, score, kk, prune_key=prune, want_kth_key=True)
         self.u, self.v = ops.gather_pairs2(None if self.score is None else (self.u, self.v), (pu, pv), idx)
         self.score = sc
+        self.kth_key = kth if kk == self.k else None
+
+    def pool(self):
+        """Band mode: (edges int32 [2,P], score fp32 [P]) of the final pool, candidate order."""
+        self.rethreshold()
+        if self.score is None:
+            return None, None
+        return torch.stack([self.u, self.v]), self.score
 
     def result(self, device=None) -> torch.Tensor:
         if self.score is None or self.score.numel() == 0:
             return torch.empty((0, 3), dtype=torch.float32, device=device)
-        return ops.topk_edges(torch.stack([self.u, self.v]), self.score, self.score.numel())
+        k = self.score.numel() if self.k is None else min(self.k, self.score.numel())
+        return ops.topk_edges(torch.stack([self.u, self.v]), self.score, k)
+
+
+class FilterJob:
+    """One filter model of a ``filter_topk_multi`` call: ``name`` in models.SUPPORTED_MODELS, the model
+    object (``LinkGNN`` / ``CommonNeighborsPredictor``), optionally the rebuilt RA graph (filter.py:130-139)
+    and, for the GNN models, the K2 arm:
+
+      ``"fp32"``       reference arithmetic on FFMA for every candidate;
+      ``"bf16"``       the tcgen05 arm alone — scores within PREFILTER_TOL, list approximately the fp32 one;
+      ``"prefilter"``  the tcgen05 arm as a PREFILTER and the fp32 arm on its survivors: the fp32 arm's
+                       exact proposal list at tensor-core speed (default)."""
+
+    def __init__(self, name: str, model, ra_adj: Optional[SparseAdj] = None, precision: Optional[str] = None):
+        self.name, self.model, self.ra_adj = name, model, ra_adj
+        if precision is None and name in GNN_MODELS:
+            precision = getattr(model.linkpred, "precision", None) or "prefilter"
+        self.precision = precision
+
+
+def tc_arm_supported(model) -> bool:
+    """Shapes the tcgen05 arm is built for (csrc/linkpred_tc.cu): >= 2 layers, H in {64, 128, 256}."""
+    lp = model.linkpred
+    return len(lp.lins) >= 2 and lp.lins[0].in_features in (64, 128, 256)
+
+
+@torch.no_grad()
+def filter_topk_multi(jobs, x, adj: SparseAdj, k: Optional[int] = None, slab_pairs: int = 1 << 27,
+                      distributed: bool = False, stats: Optional[dict] = None, pushdown: bool = True,
+                      owners: Optional[Tuple[int, int]] = None):
+    """The filter step for several filter models over ONE enumeration of the 2-hop candidates: a list of
+    sorted proposal lists (float32 ``[k,3]`` rows (u, v, score) on the device; score descending, ties by
+    the reference's candidate order), one per job.  ``k=None`` keeps every candidate like the reference.
+
+    GNN jobs with ``precision="prefilter"``: every candidate is scored by the tcgen05 arm (bf16 operands)
+    and the running pool keeps all candidates whose bf16 score is within ``2 * PREFILTER_TOL`` of the
+    running k-th best bf16 score T16.  With |s16 - s32| <= tol for every pair, the k candidates with the
+    best s16 all have s32 >= T16 - tol, so a candidate with s16 < T16 - 2 tol (hence s32 < T16 - tol) cannot
+    be among the k best by s32: the pool contains the fp32 arm's top-k.  The pool (~k candidates) is then
+    re-scored by the fp32 arm and sorted — the result is the fp32 arm's list bit for bit.  The tolerance
+    itself is checked on the pool (millions of pairs next to the boundary); a violation raises
+    ``PrefilterToleranceError`` (``filter_topk`` then re-runs the job on the fp32 arm).
+
+    ``owners=(lo, hi)`` restricts the candidates to those owned by v in [lo, hi) (a sample of the job)."""
+    rank, world = parallel.world_info() if distributed else (0, 1)
+    if world > 1 and k is None:
+        raise ValueError("distributed filter needs a proposal size k")
+    jobs = [j if isinstance(j, FilterJob) else FilterJob(*j) for j in jobs]
+    ph = _Phases(stats is not None and bool(stats.get("time_phases")))
+    o_lo, o_hi = (0, adj.n) if owners is None else (max(int(owners[0]), 0), min(int(owners[1]), adj.n))
+    v_lo, v_hi = o_lo, o_hi
+    if world > 1:
+        bounds = parallel.partition_by_work(candidates.two_path_work(adj)[o_lo:o_hi], world)
+        v_lo, v_hi = o_lo + bounds[rank], o_lo + bounds[rank + 1]
+    # per job: scoring plan + running proposal set
+    plans = []
+    fused_job = None
+    for j in jobs:
+        if j.name in GNN_MODELS:
+            assert isinstance(j.model, LinkGNN)
+            prec = j.precision
+            if prec in ("prefilter", "bf16") and not tc_arm_supported(j.model):
+                prec = "fp32"                                # shapes the tcgen05 arm is not built for (H=300)
+            if prec == "prefilter" and k is None:
+                prec = "fp32"                                # keeping every candidate: nothing to prefilter
+            h = j.model.embed(x, adj, distributed=world > 1)
+            plans.append(dict(kind="gnn", prec=prec, h=h, ctx=None if prec == "fp32" else j.model.linkpred.tc_context(h),
+                              run=RunningTopK(k, 2.0 * PREFILTER_TOL if prec == "prefilter" else None, pushdown)))
+        else:
+            table = heuristic_table(j.name, adj, j.ra_adj)
+            if table is not None and fused_job is None:
+                fused_job = len(plans)
+            plans.append(dict(kind="heuristic", table=table, run=RunningTopK(k, None, pushdown)))
+    ph.mark("embed")
+    n_slabs = 0
+    for lo, hi, cap in iter_slabs(adj, v_lo, v_hi, slab_pairs):
+        n_slabs += 1
+        scores = {}
+        if fused_job is not None:
+            # CN / AA / RA are the values of A@A: one walk over the owners' 2-paths yields the
+            # candidates and their scores together (bit-identical to scoring the pairs with K3)
+            t = plans[fused_job]["table"]
+            edges, scores[fused_job] = candidates.two_hop_scored(t[0], t[1], lo, hi, sigmoid=t[2], cap=cap,
+                                                                 use_values=t[3])
+            ph.mark("enum_score")
+        else:
+            edges = candidates.two_hop(adj, lo, hi, cap=cap)
+            ph.mark("enum")
+        if edges.shape[1] == 0:
+            continue
+        for i, (j, p) in enumerate(zip(jobs, plans)):
+            if i in scores:
+                continue
+            if p["kind"] == "gnn":
+                scores[i] = (j.model.linkpred.score_pairs(p["h"], edges, "fp32") if p["prec"] == "fp32"
+                             else p["ctx"].score(edges))
+                ph.mark("mlp")
+            else:
+                scores[i] = score_edges(j.name, j.model, x, adj, edges, True, j.ra_adj)
+                ph.mark("score")
+        for i, p in enumerate(plans):
+            p["run"].update(edges, scores[i])
+        ph.mark("topk")
+        del edges, scores
+    out = []
+    for j, p in zip(jobs, plans):
+        run = p["run"]
+        if p["kind"] == "gnn" and p["prec"] == "prefilter":
+            res, info = _rescore_pool(j.model, p["h"], run, k, world)
+            if stats is not None:
+                stats.setdefault("prefilter", {})[j.name] = info
+            ph.mark("rescore")
+        else:
+            res = run.result(adj.device)
+            ph.mark("topk")
+        if world > 1:
+            res = parallel.merge_topk(res, k)
+            ph.mark("merge")
+        out.append(res)
+    if stats is not None:
+        stats["candidates_scored"] = plans[0]["run"].seen if plans else 0
+        stats["slabs"] = n_slabs
+        stats["owners"] = [v_lo, v_hi]
+        stats["pushdown_survivors"] = [p["run"].survivors for p in plans]
+        if ph.on:
+            torch.cuda.synchronize()
+            stats["phase_ms"] = ph.totals()
+    return out
+
+
+def _rescore_pool(model, h, run: RunningTopK, k: int, world: int):
+    """Prefilter epilogue: fp32 scores of the pool, tolerance check, exact top-k of the fp32 scores."""
+    edges, s16 = run.pool()
+    dev = h.device
+    margin = 2.0 * PREFILTER_TOL
+    pool_local = 0 if s16 is None else s16.numel()
+    if world > 1:
+        # the global k-th bf16 score bounds every rank's pool from below (it is >= each local k-th)
+        if s16 is None:
+            s16 = torch.empty(0, dtype=torch.float32, device=dev)
+            edges = torch.empty((2, 0), dtype=torch.int32, device=dev)
+        gkey = parallel.global_kth_key(s16, k)
+        u, v, s16 = ops.threshold_compact(s16, edges, gkey, margin, inclusive=True)
+        edges = torch.stack([u, v])
+    P = 0 if s16 is None else s16.numel()
+    info = dict(k=int(k), pool=int(P), pool_before_exchange=int(pool_local), tol=PREFILTER_TOL, margin=margin,
+                band_occupancy=float(P) / max(int(k), 1))
+    res = torch.empty((0, 3), dtype=torch.float32, device=dev)
+    dev_max = torch.zeros(1, dtype=torch.float32, device=dev)
+    if P:
+        s32 = model.linkpred.score_pairs(h, edges, "fp32")
+        dev_max = (s32 - s16).abs().max().reshape(1)
+        res = ops.topk_edges(edges, s32, min(int(k), P))
+    if world > 1:                                            # every rank must take the same decision
+        torch.distributed.all_reduce(dev_max, op=torch.distributed.ReduceOp.MAX)
+    info["max_abs_dev_bf16_vs_fp32"] = float(dev_max.item())
+    if not info["max_abs_dev_bf16_vs_fp32"] <= PREFILTER_TOL:
+        raise PrefilterToleranceError(f"bf16 prefilter scores deviate {info['max_abs_dev_bf16_vs_fp32']:.3e} from fp32 "
+                                      f"(> {PREFILTER_TOL:.1e})")
+    return res, info
 
 
 @torch.no_grad()
 def filter_topk(model_name: str, model, x, adj: SparseAdj, k: Optional[int] = None,
                 slab_pairs: int = 1 << 27, distributed: bool = False, ra_adj: Optional[SparseAdj] = None,
-                stats: Optional[dict] = None) -> torch.Tensor:
-    """Sorted proposal list, float32 ``[k,3]`` rows (u, v, score) on the device: score descending,
-    ties by the reference's candidate order.  ``k=None`` keeps every candidate like the reference."""
-    rank, world = parallel.world_info() if distributed else (0, 1)
-    v_lo, v_hi = 0, adj.n
-    if world > 1:
-        bounds = parallel.partition_by_work(candidates.two_path_work(adj), world)
-        v_lo, v_hi = bounds[rank], bounds[rank + 1]
-    running = RunningTopK(k)
-    fused = heuristic_table(model_name, adj, ra_adj) if model_name not in GNN_MODELS else None
-    for lo, hi, cap in iter_slabs(adj, v_lo, v_hi, slab_pairs):
-        if fused is not None:
-            # CN / AA / RA are the values of A@A: one walk over the owners' 2-paths yields the
-            # candidates and their scores together (bit-identical to scoring the pairs with K3)
-            edges, score = candidates.two_hop_scored(fused[0], fused[1], lo, hi, sigmoid=fused[2], cap=cap,
-                                                     use_values=fused[3])
-        else:
-            edges = candidates.two_hop(adj, lo, hi, cap=cap)
-            if edges.shape[1]:
-                score = score_edges(model_name, model, x, adj, edges, True, ra_adj)
-        if edges.shape[1]:
-            running.update(edges, score)
-        del edges
-    n_scored = running.seen
-    running = running.result(adj.device)
-    if stats is not None:
-        stats["candidates_scored"] = n_scored
-    if world > 1:
-        assert k is not None, "distributed filter needs a proposal size k"
-        running = parallel.merge_topk(running, k)
-    return running
+                stats: Optional[dict] = None, precision: Optional[str] = None,
+                owners: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+    """Sorted proposal list of one filter model, float32 ``[k,3]`` rows (u, v, score) on the device: score
+    descending, ties by the reference's candidate order.  ``k=None`` keeps every candidate like the
+    reference.  ``precision`` (GNN models): see ``FilterJob``; default = the model's ``linkpred.precision``."""
+    job = FilterJob(model_name, model, ra_adj, precision)
+    try:
+        return filter_topk_multi([job], x, adj, k, slab_pairs, distributed, stats, owners=owners)[0]
+    except PrefilterToleranceError as exc:
+        import warnings
+        warnings.warn(f"{exc}; re-running the filter step on the fp32 arm")
+        job.precision = "fp32"
+        if stats is not None:
+            stats["prefilter_fallback"] = str(exc)
+        return filter_topk_multi([job], x, adj, k, slab_pairs, distributed, stats, owners=owners)[0]
 
 
 def load_extra_edges(path: str, num_sorted_edge: int) -> torch.Tensor:

@@ -17,9 +17,12 @@ same code builds the graph on ``cuda:k`` for the kernels and on the CPU for host
 """
 from __future__ import annotations
 
+import itertools
 from typing import Optional
 
 import torch
+
+_UID = itertools.count(1)
 
 
 class SparseAdj:
@@ -30,6 +33,7 @@ class SparseAdj:
         if self.val is not None:
             self.val = self.val.contiguous()
         self._cache = {}
+        self.uid = next(_UID)           # identity of this graph object for caches (never reused, unlike id())
 
     # -- torch_sparse.SparseTensor look-alikes used on the path -------------------------------
     @property

@@ -32,7 +32,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import autograd, ops
+from . import autograd, ops, parallel
 from .graph import SparseAdj
 
 GNN_MODELS = ("gcn", "sage")
@@ -62,6 +62,16 @@ class GCNConv(nn.Module):
             return torch.relu(out) if relu else out
         return ops.spmm_csr(rowptr, col, val, xw, "sum", self.bias, relu)
 
+    @torch.no_grad()
+    def forward_rows(self, x_rows: torch.Tensor, adj: SparseAdj, bounds, rank: int, relu: bool) -> torch.Tensor:
+        """Rows [bounds[rank], bounds[rank+1]) of the layer output from the same rows of its input (scoring
+        path): x·W for the local row blocks (cuBLAS fp32), all-gather of the ``n/G x H`` slabs, K1 over the
+        local rows of the normalised matrix with bias / ReLU fused."""
+        lo, hi = bounds[rank], bounds[rank + 1]
+        rowptr, col, val = adj.gcn_norm()
+        xw = parallel.allgather_row_slabs(parallel.block_matmul(x_rows, self.weight, lo, hi, adj.n), bounds)
+        return ops.spmm_csr(rowptr[lo:hi + 1], col, val, xw, "sum", self.bias, relu)
+
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
         # PyG >= 2.0 stores GCNConv's weight as ``lin.weight [out,in]`` (SURVEY §8f row 4)
         k2 = prefix + "lin.weight"
@@ -90,6 +100,18 @@ class SAGEConv(nn.Module):
         out = self.lin_l(agg) + self.lin_r(x)
         return torch.relu(out) if relu else out
 
+    @torch.no_grad()
+    def forward_rows(self, x_rows: torch.Tensor, adj: SparseAdj, bounds, rank: int, relu: bool) -> torch.Tensor:
+        """Row-sharded scoring-path forward (see GCNConv.forward_rows): the layer INPUT is all-gathered, the
+        neighbour mean (K1) and the two dense products run on the local rows only."""
+        lo, hi = bounds[rank], bounds[rank + 1]
+        x_full = parallel.allgather_row_slabs(x_rows, bounds)
+        agg = ops.spmm_csr(adj.rowptr[lo:hi + 1], adj.col, None, x_full, "mean")
+        out = parallel.block_matmul(agg, self.lin_l.weight.t(), lo, hi, adj.n)
+        out += self.lin_l.bias
+        out += parallel.block_matmul(x_rows.contiguous(), self.lin_r.weight.t(), lo, hi, adj.n)
+        return torch.relu_(out) if relu else out
+
 
 class _ConvStack(nn.Module):
     conv_cls = None
@@ -113,6 +135,22 @@ class _ConvStack(nn.Module):
         return x
 
 
+    @torch.no_grad()
+    def embed_rows(self, x: torch.Tensor, adj: SparseAdj, rank: int = 0, world: int = 1) -> torch.Tensor:
+        """Scoring-path forward, row-sharded over ``world`` ranks (world == 1: the same code on one GPU).
+        Rank r owns a block-aligned row range of near-equal nnz (parallel.row_partition); per layer one
+        all-gather of ``n/G x H`` fp32 slabs; the result is the full ``h`` on every rank, bit-identical
+        for every world size (same row blocks in the dense products, same per-row order in K1)."""
+        rowptr = adj.gcn_norm()[0] if self.conv_cls is GCNConv else adj.rowptr
+        bounds = parallel.row_partition(rowptr, adj.n, world)
+        lo, hi = bounds[rank], bounds[rank + 1]
+        xr = x[lo:hi].contiguous().float()
+        last = len(self.convs) - 1
+        for i, conv in enumerate(self.convs):
+            xr = conv.forward_rows(xr, adj, bounds, rank, relu=i != last)
+        return parallel.allgather_row_slabs(xr, bounds).contiguous()
+
+
 class GCN(_ConvStack):
     conv_cls = GCNConv
 
@@ -127,16 +165,26 @@ class LinkPredictor(nn.Module):
         dims = [in_channels] + [hidden_channels] * (num_layers - 1) + [out_channels]
         self.lins = nn.ModuleList(nn.Linear(dims[i], dims[i + 1]) for i in range(num_layers))
         self.dropout = dropout
-        self.precision = "fp32"
+        # K2 arm: "prefilter" (default) = fp32 results everywhere; the filter step additionally uses the tcgen05
+        # arm to preselect the band around its top-k (filter_step.FilterJob); "fp32" / "bf16" force one arm
+        self.precision = "prefilter"
 
     def reset_parameters(self):
         for lin in self.lins:
             lin.reset_parameters()
 
-    def score_pairs(self, h: torch.Tensor, edges: torch.Tensor) -> torch.Tensor:
-        """sigmoid(MLP(h[u]*h[v])) for edges [2,B] -> [B]; gather fused into the kernel."""
+    def score_pairs(self, h: torch.Tensor, edges: torch.Tensor, precision: Optional[str] = None) -> torch.Tensor:
+        """sigmoid(MLP(h[u]*h[v])) for edges [2,B] -> [B]; gather fused into the kernel.  ``precision``:
+        "fp32" (FFMA, reference arithmetic) or "bf16" (tcgen05); default ``self.precision`` ("prefilter", the
+        filter step's two-stage mode, scores a plain pair list in fp32)."""
+        prec = precision or self.precision
         return ops.linkpred_mlp(h, edges, [l.weight for l in self.lins], [l.bias for l in self.lins],
-                                precision=self.precision, sigmoid=True)
+                                precision="fp32" if prec == "prefilter" else prec, sigmoid=True)
+
+    def tc_context(self, h: torch.Tensor) -> "ops.LinkpredTC":
+        """The tcgen05 arm bound to ``h`` and the current weights for a series of slabs (bf16 table and weight
+        images built once): ``ctx.score(edges)`` == ``score_pairs(h, edges, "bf16")``."""
+        return ops.LinkpredTC(h, [l.weight for l in self.lins], [l.bias for l in self.lins])
 
     def forward(self, x_i, x_j):
         """Reference signature (two gathered [B,H] blocks) kept for callers that use it."""
@@ -175,12 +223,18 @@ class LinkGNN(nn.Module):
         return x
 
     @torch.no_grad()
-    def embed(self, x, adj: SparseAdj) -> torch.Tensor:
-        """h = gnn(input, adj), cached on (graph identity, input identity, parameter versions)."""
-        key = (id(adj), None if x is None else (x.data_ptr(), x._version),
+    def embed(self, x, adj: SparseAdj, distributed: bool = False) -> torch.Tensor:
+        """h = gnn(input, adj) in eval arithmetic (dropout off), cached on (graph uid, input identity,
+        parameter versions).  ``distributed``: row-sharded over the ranks of the default process group and
+        all-gathered (every rank ends up with the full h, the same bits as on one GPU).  While the module
+        is in training mode nothing is cached (a later eval call must not see dropout-perturbed h)."""
+        rank, world = parallel.world_info() if distributed else (0, 1)
+        key = (adj.uid, None if x is None else (x.data_ptr(), x._version),
                tuple((p.data_ptr(), p._version) for p in self.parameters()))
+        if self.training:
+            return self.gnn(self._input(x), adj).contiguous()
         if key != self._h_key:
-            self._h = self.gnn(self._input(x), adj).contiguous()
+            self._h = self.gnn.embed_rows(self._input(x), adj, rank, world)
             self._h_key = key
         return self._h
 
@@ -239,7 +293,7 @@ def build_model(args, data, device):
         gnn = cls(input_dim, args.hidden_channels, args.hidden_channels, args.num_layers, args.dropout).to(device)
         linkpred = LinkPredictor(args.hidden_channels, args.hidden_channels, 1, args.num_layers,
                                  args.dropout).to(device)
-        linkpred.precision = getattr(args, "mlp_precision", None) or "fp32"
+        linkpred.precision = getattr(args, "mlp_precision", None) or "prefilter"
         return LinkGNN(emb, gnn, linkpred)
     return CommonNeighborsPredictor(emb, input_dim, args.hidden_channels, args.hidden_channels,
                                     args.num_layers, args.dropout, model_type=args.model).to(device)

@@ -10,7 +10,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import (EPS_CN_GROUPED_BY_V, EPS_CN_SIGMOID, EPS_MLP_FP32, EPS_MLP_TC_BF16,
+from ._lib import (EPS_CN_GROUPED_BY_V, EPS_CN_SIGMOID, EPS_MLP_FP32, EPS_MLP_REUSE_WORKSPACE, EPS_MLP_TC_BF16,
                    EPS_REDUCE_MEAN, EPS_REDUCE_SUM, EpsError, check)
 from .graph import SparseAdj
 
@@ -89,6 +89,8 @@ def cn_aa(adj: SparseAdj, edges: torch.Tensor, wtable: Optional[torch.Tensor] = 
     """K3.  score[i] = sum_{k in N(u)&N(v)} a_u (a_v w_k); optional exact int32 counts."""
     _need_cuda(adj.col, edges, wtable)
     lib = _lib.load()
+    from .candidates import check_fixed_point_range
+    check_fixed_point_range(adj, wtable, use_values)
     pu, pv = _pairs(edges)
     M = pu.numel()
     score = torch.empty(M, dtype=torch.float32, device=adj.device)
@@ -127,6 +129,44 @@ def linkpred_mlp(h: torch.Tensor, edges: torch.Tensor, weights: Sequence[torch.T
                                _ptr(score), _ptr(ws), ws.numel(), _stream()), "eps_linkpred_mlp")
     LAUNCHES["n"] += ((3 if M >= 2 * n else 2) if prec == EPS_MLP_TC_BF16 else 1) if M else 0
     return score
+
+
+class LinkpredTC:
+    """K2's tcgen05 arm bound to ONE embedding matrix and ONE set of weights for a series of calls (the ~100
+    owner slabs of a filter job): the bf16 copy of ``h`` and the packed weight images live in a workspace this
+    object owns and are built by the first long call only (EPS_MLP_REUSE_WORKSPACE afterwards).  ``h`` and the
+    weights are held by reference and must not be modified while the object is in use.  Same scores, bit for
+    bit, as ``linkpred_mlp(..., precision="bf16")``."""
+
+    def __init__(self, h: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor]):
+        _need_cuda(h, *weights, *biases)
+        self.h = h.contiguous().float()
+        self.Ws = [w.detach().contiguous().float() for w in weights]
+        self.bs = [b.detach().contiguous().float() for b in biases]
+        self.ws = None
+        self.prepared = False
+
+    def score(self, edges: torch.Tensor, sigmoid: bool = True) -> torch.Tensor:
+        lib = _lib.load()
+        n, H = self.h.shape
+        L = len(self.Ws)
+        pu, pv = _pairs(edges)
+        M = pu.numel()
+        if M < 2 * n:                      # short list: no bf16 table in the workspace, nothing to reuse
+            return linkpred_mlp(self.h, edges, self.Ws, self.bs, "bf16", sigmoid)
+        need = int(lib.eps_linkpred_workspace_bytes(n, H, L, M, EPS_MLP_TC_BF16))
+        if self.ws is None or self.ws.numel() < need:
+            self.ws = _ws(need + (M // 256) * 2, self.h.device)      # headroom for somewhat longer slabs
+            self.prepared = False
+        Wp = (C.c_void_p * L)(*[w.data_ptr() for w in self.Ws])
+        bp = (C.c_void_p * L)(*[b.data_ptr() for b in self.bs])
+        score = torch.empty(M, dtype=torch.float32, device=self.h.device)
+        prec = EPS_MLP_TC_BF16 | (EPS_MLP_REUSE_WORKSPACE if self.prepared else 0)
+        check(lib.eps_linkpred_mlp(_ptr(self.h), n, H, _ptr(pu), _ptr(pv), M, Wp, bp, L, prec, int(sigmoid),
+                                   _ptr(score), _ptr(self.ws), self.ws.numel(), _stream()), "eps_linkpred_mlp")
+        LAUNCHES["n"] += 1 if self.prepared else 3
+        self.prepared = True
+        return score
 
 
 def topk(score: torch.Tensor, k: int):
@@ -193,6 +233,78 @@ def topk_select2(score_a: Optional[torch.Tensor], score_b: torch.Tensor, k: int,
                                    _ptr(out), _ptr(ws), ws.numel(), _stream()), "eps_topk_select2_f32")
     LAUNCHES["n"] += _SELECT_LAUNCHES
     return (idx, out, kth) if want_kth_key else (idx, out)
+
+
+def kth_key(score: torch.Tensor, k: int) -> torch.Tensor:
+    """Order key (int32 [1], device) of the k-th best score: the three histogram passes of K4 only."""
+    _need_cuda(score)
+    lib = _lib.load()
+    M = score.numel()
+    assert score.dtype == torch.float32 and score.is_contiguous() and 1 <= k <= M
+    kth = torch.empty(1, dtype=torch.int32, device=score.device)
+    ws = _ws(lib.eps_topk_workspace_bytes(M, k), score.device)
+    check(lib.eps_topk_select2_f32(None, 0, _ptr(score), M, k, None, _ptr(kth), None, None, _ptr(ws), ws.numel(),
+                                   _stream()), "eps_topk_select2_f32")
+    LAUNCHES["n"] += 6
+    return kth
+
+
+def key_to_score(key) -> float:
+    """Host value of the score an order key stands for (the inverse of K4's key map)."""
+    import numpy as np
+    kk = int(key.item() if hasattr(key, "item") else key) & 0xFFFFFFFF
+    asc = ~kk & 0xFFFFFFFF
+    bits = (asc ^ 0x80000000) if asc >> 31 else (~asc & 0xFFFFFFFF)
+    return float(np.array([bits], dtype=np.uint32).view(np.float32)[0])
+
+
+def score_to_key(score: float) -> int:
+    """K4's order key of a score (ascending key == descending score, -0.0 folded into +0.0)."""
+    import numpy as np
+    b = int((np.array([score], dtype=np.float32) + np.float32(0.0)).view(np.uint32)[0])
+    asc = b ^ (0xFFFFFFFF if b >> 31 else 0x80000000)
+    return ~asc & 0xFFFFFFFF
+
+
+def key_tensor(key: int, device) -> torch.Tensor:
+    """A uint32 order key as the int32 [1] device tensor the kernels read."""
+    key = int(key) & 0xFFFFFFFF
+    return torch.tensor([key - 2**32 if key >= 2**31 else key], dtype=torch.int32, device=device)
+
+
+def threshold_compact(score: torch.Tensor, edges: Optional[torch.Tensor], bound_key: torch.Tensor,
+                      margin: float = 0.0, inclusive: bool = False, want_pos: bool = False):
+    """K4b.  The elements of ``score`` that beat the running k-th score (``bound_key``), in position order:
+    ``(u, v, score)`` int32/int32/fp32 (+ positions with ``want_pos``; ``edges=None`` skips the pairs).
+    ``inclusive=False``: strictly better; ``inclusive=True``: ``score >= s_k - margin``.
+    One host sync (the survivor count sizes the outputs)."""
+    _need_cuda(score, edges, bound_key)
+    lib = _lib.load()
+    M = score.numel()
+    dev = score.device
+    assert score.dtype == torch.float32 and score.is_contiguous() and bound_key.dtype == torch.int32
+    pu = pv = None
+    if edges is not None:
+        pu, pv = _pairs(edges)
+        assert pu.numel() == M
+    nt = int(lib.eps_threshold_tiles(M))
+    off = torch.empty(nt + 1, dtype=torch.int32, device=dev)
+    ws = _ws(lib.eps_threshold_workspace_bytes(M), dev)
+    check(lib.eps_threshold_count(_ptr(score), M, _ptr(bound_key), float(margin), int(inclusive), _ptr(off), _ptr(ws),
+                                  ws.numel(), _stream()), "eps_threshold_count")
+    LAUNCHES["n"] += 2 if M else 0
+    c = int(off[-1].item()) & 0xFFFFFFFF
+    ou = torch.empty(c if pu is not None else 0, dtype=torch.int32, device=dev)
+    ov = torch.empty(c if pu is not None else 0, dtype=torch.int32, device=dev)
+    osc = torch.empty(c, dtype=torch.float32, device=dev)
+    opos = torch.empty(c, dtype=torch.int32, device=dev) if want_pos else None
+    if c:
+        check(lib.eps_threshold_write(_ptr(score), _ptr(pu), _ptr(pv), M, _ptr(bound_key), float(margin), int(inclusive),
+                                      _ptr(off), _ptr(ou) if pu is not None else None,
+                                      _ptr(ov) if pu is not None else None, _ptr(osc), _ptr(opos), _stream()),
+              "eps_threshold_write")
+        LAUNCHES["n"] += 1
+    return (ou, ov, osc, opos) if want_pos else (ou, ov, osc)
 
 
 def gather_pairs2(pairs_a, pairs_b, idx: torch.Tensor):

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define EPS_VERSION 100 /* 0.1.0 */
+#define EPS_VERSION 200 /* 0.2.0; edge_proposal_sets_b200/_lib.py checks it at load time */
 
 typedef enum {
   EPS_OK = 0,
@@ -123,6 +123,12 @@ size_t eps_cn_aa_workspace_bytes(void);
  * ------------------------------------------------------------------------- */
 #define EPS_MLP_FP32 0
 #define EPS_MLP_TC_BF16 1
+/* OR-ed into `precision` with EPS_MLP_TC_BF16: `workspace` is the buffer of an EARLIER call with the same h
+ * (contents), weights, n, H and L, and both calls have M >= 2n (the bf16 copy of h exists) — the bf16 table
+ * and the weight images in it are reused instead of rebuilt (one filter job scores ~100 slabs against the
+ * same embeddings).  The workspace must be at least eps_linkpred_workspace_bytes(n, H, L, M_max, ...) for
+ * the largest M of the series; its layout does not depend on M except for the tail. */
+#define EPS_MLP_REUSE_WORKSPACE 0x100
 int eps_linkpred_mlp(const float *h, int32_t n, int32_t H, const int32_t *pair_u,
                      const int32_t *pair_v, int64_t M, const float *const *W_h,
                      const float *const *b_h, int32_t L, int precision, int apply_sigmoid,
@@ -175,6 +181,38 @@ int eps_topk_select2_f32(const float *score_a, int64_t Ma, const float *score_b,
 int eps_gather_pairs2(const int32_t *ua, const int32_t *va, int64_t Ma, const int32_t *ub,
                       const int32_t *vb, const uint32_t *idx, int64_t k, int32_t *out_u, int32_t *out_v,
                       void *stream);
+
+/* ---------------------------------------------------------------------------
+ * K4b  threshold push-down: ordered compaction of a slab under the running k-th score
+ * replaces: the same global sort (filter.py:160-161).  Once the running list
+ *           holds k candidates, only slab elements that beat its k-th score
+ *           can enter it; selecting them with one counting read and one
+ *           writing read replaces the five radix-select reads of the slab.
+ *   bound_key  device uint32: order key of the k-th score s_k (kth_key_out of
+ *              eps_topk_select2_f32)
+ *   inclusive == 0 : survive iff score > s_k STRICTLY — a slab tie at s_k comes
+ *                    later in candidate order than every tie already in the
+ *                    list, so by the tie rule it can never displace one
+ *   inclusive != 0 : survive iff score >= s_k - margin (margin >= 0): the
+ *                    prefilter band of the bf16 tensor-core arm, whose
+ *                    survivors are re-scored in fp32 (filter_step.py)
+ *   count: tile_offsets[eps_threshold_tiles(M) + 1] (device) = exclusive scan of
+ *          the per-tile survivor counts; the last entry is the total, which the
+ *          host reads to size the outputs
+ *   write: the survivors in POSITION ORDER: (u, v), score and/or position
+ *          (any of out_u+out_v / out_score / out_pos may be NULL)
+ * eps_topk_select2_f32 with out_idx == out_score == NULL and kth_key_out set
+ * returns only the k-th key (re-thresholding of a band pool).
+ * ------------------------------------------------------------------------- */
+int64_t eps_threshold_tiles(int64_t M);
+size_t eps_threshold_workspace_bytes(int64_t M);
+int eps_threshold_count(const float *score, int64_t M, const uint32_t *bound_key, float margin,
+                        int inclusive, uint32_t *tile_offsets, void *workspace, size_t workspace_bytes,
+                        void *stream);
+int eps_threshold_write(const float *score, const int32_t *pair_u, const int32_t *pair_v, int64_t M,
+                        const uint32_t *bound_key, float margin, int inclusive,
+                        const uint32_t *tile_offsets, int32_t *out_u, int32_t *out_v, float *out_score,
+                        uint32_t *out_pos, void *stream);
 
 /* ---------------------------------------------------------------------------
  * K6  2-hop candidate enumeration for the owner range [v_lo, v_hi)

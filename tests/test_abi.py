@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     lib = C.CDLL(_lib.LIB_PATH)
     for name in header_functions():
         assert hasattr(lib, name), f"{name} declared in include/eps.h but not exported"
-    assert _lib.load().eps_version() == 100
+    assert _lib.load().eps_version() == _lib.EPS_VERSION
 
 
 def test_argument_validation_needs_no_device():

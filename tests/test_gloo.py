@@ -54,6 +54,38 @@ def _worker(rank, world, port, out):
         # a rank owning fewer than k candidates pads with -inf rows that never surface
         short = parallel.pad_rows(torch.from_numpy(results["cn"][1][:5]), 8)
         ok = ok and short.shape == (8, 3) and bool(torch.isinf(short[5:, 2]).all())
+        # ---- global k-th score exchange: two all-reduced histograms == k-th key of the concatenation ----
+        rng = np.random.default_rng(7 + rank)
+        for scores, kk in ((rng.standard_normal(5000).astype(np.float32), 1234),
+                           (rng.integers(0, 6, 4000).astype(np.float32), 3999),          # tie-heavy CN-like scores
+                           (np.array([0.5, -0.0, 0.0, np.inf, -np.inf, 1.0], np.float32), 7),
+                           (rng.random(10).astype(np.float32), 500)):                     # fewer than k in total
+            t = torch.from_numpy(scores)
+            both = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(both, t)
+            allk = np.sort(parallel.order_keys(torch.cat(both)).numpy())
+            want = int(allk[kk - 1]) if kk <= allk.size else 0xFFFFFFFF
+            got = int(parallel.global_kth_key(t, kk).item()) & 0xFFFFFFFF
+            ok = ok and got == want
+        # order_keys is the device kernel's key map (ops.score_to_key restates csrc/topk.cu score_key)
+        from edge_proposal_sets_b200 import ops
+        probe = np.array([1.5, 0.0, -0.0, -3.25, 1e-30, np.inf], np.float32)
+        ok = ok and [int(x) for x in parallel.order_keys(torch.from_numpy(probe))] == [ops.score_to_key(float(x)) for x in probe]
+        ok = ok and all(ops.key_to_score(ops.score_to_key(float(x))) == float(x) + 0.0 for x in probe)
+        # ---- row-sharded embeddings plumbing: block-aligned nnz partition, uneven slabs gathered in place ----
+        n = g.n
+        R = parallel.row_block(n)
+        rb = parallel.row_partition(adj.rowptr, n, world)
+        ok = ok and rb[0] == 0 and rb[-1] == n and all(b % R == 0 or b == n for b in rb) and rb == sorted(rb)
+        full = torch.arange(n * 3, dtype=torch.float32).reshape(n, 3)
+        for bnds in (rb, [0, R, n], [0, n, n]):
+            got = parallel.allgather_row_slabs(full[bnds[rank]:bnds[rank + 1]].clone(), bnds)
+            ok = ok and torch.equal(got, full)
+        xw = torch.randn(n, 8, generator=torch.Generator().manual_seed(1))
+        wmat = torch.randn(8, 5, generator=torch.Generator().manual_seed(2))
+        mine_rows = parallel.block_matmul(xw[rb[rank]:rb[rank + 1]], wmat, rb[rank], rb[rank + 1], n)
+        whole = parallel.block_matmul(xw, wmat, 0, n, n)
+        ok = ok and torch.equal(mine_rows, whole[rb[rank]:rb[rank + 1]])       # a row's bits do not depend on the shard
         out[rank] = ok
     finally:
         dist.destroy_process_group()

@@ -100,3 +100,57 @@ def test_email_shape_cn_filter_then_cn_rank(tmp_path):
                          "--runs", "1"], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=150)
     assert r2.returncode == 0, r2.stderr[-2000:]
     assert "Using 1500 highest scoring edges" in r2.stdout and "Hits@20" in r2.stdout
+
+
+@pytest.mark.timeout(280)
+def test_twitch_sage_filter_with_real_features_then_aa_rank_sweep(tmp_path):
+    """BASELINE configs[2]: SAGE filter on twitch-DE with the real 2,514-column binary features (layer-1
+    neighbour mean over 2,770-wide rows) -> proposal list -> Adamic-Adar rank with a proposal-size sweep.
+    The checkpoint is written in the reference's state-dict layout (models/{dataset}_{model}||0|0.pt)."""
+    import argparse
+    from oracle import gnn as ognn
+    from edge_proposal_sets_b200.data import get_data
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    torch.manual_seed(0)
+    edge_index, edge_weight, split_edge, data = get_data(argparse.Namespace(dataset="twitch", use_feature=True), "cpu")
+    assert tuple(data.x.shape) == (9498, 2514) and float(data.x.sum()) == 193132.0
+    n, H, L = data.num_nodes, 256, 3
+    sd = ognn.random_state_dict("sage", n, data.x.shape[1], H, L, seed=4)
+    (tmp_path / "models").mkdir()
+    torch.save(sd, tmp_path / "models" / "twitch_sage||0|0.pt")
+    k = 40000
+    r = subprocess.run([sys.executable, "-u", os.path.join(ROOT, "filter.py"), "--dataset", "twitch", "--model", "sage",
+                        "--checkpoint", "twitch_sage||0|0.pt", "--topk", str(k)], cwd=tmp_path, env=env,
+                       capture_output=True, text=True, timeout=250)
+    assert r.returncode == 0, r.stderr[-3000:]
+    got = torch.load(tmp_path / "filtered_edges" / "twitch_sage__0_0_sorted_edges.pt").numpy()
+    assert got.dtype == np.float32 and got.shape == (k, 3)
+    z, ei, g = golden_graph("twitch")
+    assert f"using {int(z['num_candidates'])} edges" in r.stdout
+    # fp64 oracle of the same pairs: scores within tolerance, descending, nothing from outside the band
+    xin = ognn.link_gnn_input(sd, data.x)
+    h64 = ognn.sage_forward(g, xin, sd, L, torch.float64)
+    uv = got[:, :2].astype(np.int64).T
+    sc64 = ognn.linkpred_forward(h64, uv, sd, L, torch.float64).numpy()
+    assert np.max(np.abs(got[:, 2] - sc64)) <= 2e-5
+    assert np.all(np.diff(got[:, 2]) <= 0)
+    cand = og.two_hop_candidates(g)
+    all64 = ognn.linkpred_forward(h64, cand, sd, L, torch.float64).numpy()
+    kth = np.sort(all64)[::-1][k - 1]
+    assert np.all(sc64 >= kth - 4e-5)
+    # the fp32 arm on every candidate gives the same file, bit for bit (prefilter == fp32)
+    os.link(tmp_path / "models" / "twitch_sage||0|0.pt", tmp_path / "models" / "twitch_sage||0|1.pt")
+    r32 = subprocess.run([sys.executable, "-u", os.path.join(ROOT, "filter.py"), "--dataset", "twitch", "--model", "sage",
+                          "--checkpoint", "twitch_sage||0|1.pt", "--topk", str(k), "--mlp_precision", "fp32"],
+                         cwd=tmp_path, env=env, capture_output=True, text=True, timeout=250)
+    assert r32.returncode == 0, r32.stderr[-3000:]
+    got32 = torch.load(tmp_path / "filtered_edges" / "twitch_sage__0_1_sorted_edges.pt").numpy()
+    assert np.array_equal(got, got32)
+    # rank: Adamic-Adar on the proposal-augmented graph, three sweep points (rank.py:260-272)
+    r2 = subprocess.run([sys.executable, "-u", os.path.join(ROOT, "rank.py"), "--dataset", "twitch", "--model", "adamic_ogb",
+                         "--sorted_edge_path", "twitch_sage__0_0_sorted_edges.pt", "--sweep_min", "0",
+                         "--sweep_max", "40000", "--sweep_num", "2", "--runs", "1"], cwd=tmp_path, env=env,
+                        capture_output=True, text=True, timeout=250)
+    assert r2.returncode == 0, r2.stderr[-3000:]
+    assert "Scheduled extra edges sweep: [0, 20000, 40000] x 1" in r2.stdout
+    assert r2.stdout.count("Hits@50") >= 3                       # twitch evaluates Hits@10/50/100 (train_and_eval.py:20-29)

@@ -116,3 +116,19 @@ def test_tc_arm_l2_tile_schedule_is_order_free(H, L, M):
     assert np.array_equal(natural, blocked)
     want = ognn.linkpred_forward(torch.from_numpy(h), e, sd, L, torch.float64).numpy()
     assert np.max(np.abs(blocked - want)) <= 2e-3
+
+
+@pytest.mark.timeout(120)
+def test_tc_context_reuses_table_and_weight_images():
+    """ops.LinkpredTC (bf16 table + weight images built once, EPS_MLP_REUSE_WORKSPACE afterwards) returns the
+    bits of the one-shot call for every slab of a series — longer, shorter and short-list (M < 2n) ones."""
+    from edge_proposal_sets_b200 import ops
+    H, L, n = 256, 3, 3000
+    sd, h, e, Ws, bs = _setup(H, L, n, 90000, seed=11)
+    hd, ed = torch.from_numpy(h).to(DEV), torch.from_numpy(e).to(DEV)
+    ctx = ops.LinkpredTC(hd, Ws, bs)
+    for lo, hi in [(0, 40000), (40000, 90000), (100, 20100), (5, 1005), (0, 90000)]:
+        part = ed[:, lo:hi].contiguous()
+        assert torch.equal(ctx.score(part), ops.linkpred_mlp(hd, part, Ws, bs, "bf16"))
+    assert ctx.prepared
+    assert torch.equal(ctx.score(ed, sigmoid=False), ops.linkpred_mlp(hd, ed, Ws, bs, "bf16", sigmoid=False))

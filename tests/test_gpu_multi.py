@@ -41,6 +41,34 @@ def _worker(rank, world, port, out):
         aa_single = filter_step.filter_topk("adamic_ogb", None, None, adj, k=k)
         aa_sharded = filter_step.filter_topk("adamic_ogb", None, None, adj, k=k, distributed=True)
         ok = ok and torch.equal(aa_single, aa_sharded)
+        # GCN filter: embeddings row-sharded + all-gathered == single-GPU bits; prefilter list (bf16 tcgen05 scores,
+        # global k-th exchange, fp32 re-scoring) == the single-GPU fp32-arm list
+        import argparse
+        from oracle import gnn as ognn
+        feat = s["x"].shape[1]
+        sd = ognn.random_state_dict("gcn", g.n, feat, 256, 3, seed=3)
+        args = argparse.Namespace(model="gcn", dataset="x", num_layers=3, hidden_channels=256, dropout=0.0,
+                                  use_feature=True, use_learnable_embedding=True)
+
+        class D:
+            num_nodes = g.n
+            x = torch.zeros(1, feat)
+        mg = models.build_model(args, D, dev)
+        mg.load_state_dict(sd)
+        mg.eval()
+        x = torch.from_numpy(s["x"]).to(dev)
+        h1 = mg.embed(x, adj).clone()
+        mg._h_key = None
+        h2 = mg.embed(x, adj, distributed=True)
+        ok = ok and torch.equal(h1, h2)
+        g32 = filter_step.filter_topk("gcn", mg, x, adj, k=k, precision="fp32")
+        st = {}
+        g16 = filter_step.filter_topk("gcn", mg, x, adj, k=k, precision="prefilter", distributed=True,
+                                      slab_pairs=150000, stats=st)
+        ok = ok and torch.equal(g32, g16) and "prefilter_fallback" not in st
+        both = filter_step.filter_topk_multi([filter_step.FilterJob("adamic_ogb", None), filter_step.FilterJob("gcn", mg)],
+                                             x, adj, k=k, distributed=True, slab_pairs=200000)
+        ok = ok and torch.equal(both[0], aa_single) and torch.equal(both[1], g32)
         # raw-NCCL C-ABI merge on the same local lists
         lib = _lib.load()
         idbuf = (C.c_char * 128)()

@@ -90,3 +90,83 @@ def test_running_topk_over_slabs_equals_one_global_stable_sort(k):
     got = run.result(DEV).cpu().numpy()
     want = orank.sorted_edges(e, s, None if k is None else min(k, M))
     assert got.shape == want.shape and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("pushdown", [True, False])
+@pytest.mark.parametrize("k", [5000, 123457])
+def test_running_topk_pushdown_and_legacy_select_agree(k, pushdown):
+    """K4b push-down (strictly-better survivors + select over list ++ survivors) == the plain K4 select over
+    every slab == one global stable sort; many small slabs so the k-th score rises while ties stream by."""
+    from edge_proposal_sets_b200.filter_step import RunningTopK
+    rng = np.random.default_rng(9)
+    sizes = [150000] + [40000] * 12 + [0, 3, 99999]
+    M = sum(sizes)
+    e = rng.integers(0, 60000, size=(2, M)).astype(np.int32)
+    s = rng.geometric(0.35, size=M).astype(np.float32)          # CN-like: the boundary sits inside a tie group
+    s[rng.integers(0, M, 5000)] += rng.random(5000).astype(np.float32)
+    run = RunningTopK(k, pushdown=pushdown)
+    lo = 0
+    for m in sizes:
+        run.update(torch.from_numpy(e[:, lo:lo + m]).to(DEV), torch.from_numpy(s[lo:lo + m]).to(DEV))
+        lo += m
+    got = run.result(DEV).cpu().numpy()
+    assert np.array_equal(got, orank.sorted_edges(e, s, k))
+    if pushdown:
+        assert 0 < run.survivors < M - sizes[0]                  # the push-down did prune
+
+
+@pytest.mark.parametrize("inclusive,margin", [(False, 0.0), (True, 0.0), (True, 0.25), (True, 1e-3)])
+def test_threshold_compact_vs_numpy(inclusive, margin):
+    """K4b: survivors of a slab under the running k-th score, in position order."""
+    from edge_proposal_sets_b200 import ops
+    rng = np.random.default_rng(3)
+    M = 300007
+    s = np.round(rng.standard_normal(M), 2).astype(np.float32)   # coarse values: plenty of exact ties
+    e = rng.integers(0, 1 << 20, size=(2, M)).astype(np.int32)
+    sd, ed = torch.from_numpy(s).to(DEV), torch.from_numpy(e).to(DEV)
+    for kth_score in (0.5, -0.0, 2.13, -7.0, 9.0):
+        key = ops.key_tensor(ops.score_to_key(kth_score), DEV)
+        u, v, sc, pos = ops.threshold_compact(sd, ed, key, margin, inclusive, want_pos=True)
+        if inclusive:
+            thr = np.float32(kth_score) - np.float32(margin)
+            keep = s >= (np.nextafter(thr, np.float32(-np.inf)) if margin > 0 else thr)
+            # one ulp of slack below the rounded difference is allowed (never fewer survivors than the band)
+            assert np.all(keep[pos.cpu().numpy().astype(np.int64)])
+            must = np.nonzero(s >= thr)[0]
+            assert np.all(np.isin(must, pos.cpu().numpy().astype(np.int64)))
+            want = np.nonzero(keep)[0]
+        else:
+            want = np.nonzero(s > np.float32(kth_score))[0]
+        assert np.array_equal(pos.cpu().numpy().astype(np.int64), want)
+        assert np.array_equal(sc.cpu().numpy(), s[want])
+        assert np.array_equal(u.cpu().numpy(), e[0, want]) and np.array_equal(v.cpu().numpy(), e[1, want])
+
+
+def test_kth_key_only_and_band_pool():
+    """Band mode of RunningTopK (the bf16 prefilter): the pool is exactly {score >= T_k - margin} of everything
+    seen, in candidate order, where T_k is the k-th best score."""
+    from edge_proposal_sets_b200 import ops
+    from edge_proposal_sets_b200.filter_step import RunningTopK
+    rng = np.random.default_rng(21)
+    sizes = [50000, 20000, 0, 130000, 7, 60000, 90000]
+    M, k, margin = sum(sizes), 30000, 4e-3
+    s = (1.0 / (1.0 + np.exp(-rng.standard_normal(M) * 0.4))).astype(np.float32)
+    e = np.stack([rng.integers(0, 50000, M), np.sort(rng.integers(0, 50000, M))]).astype(np.int32)
+    kth = ops.kth_key(torch.from_numpy(s).to(DEV), k)
+    T = np.sort(s)[::-1][k - 1]
+    assert ops.key_to_score(kth) == float(T)
+    run = RunningTopK(k, margin)
+    lo = 0
+    for m in sizes:
+        run.update(torch.from_numpy(e[:, lo:lo + m]).to(DEV), torch.from_numpy(s[lo:lo + m]).to(DEV))
+        lo += m
+    edges, sc = run.pool()
+    thr = np.float32(T) - np.float32(margin)
+    got_pos_ok = np.nonzero(s >= np.nextafter(thr, np.float32(-np.inf)))[0]
+    must = np.nonzero(s >= thr)[0]
+    got = sc.cpu().numpy()
+    assert must.size <= got.size <= got_pos_ok.size
+    # candidate order kept, and every element of the band is present
+    pool_set = set(map(tuple, np.stack([edges[0].cpu().numpy(), edges[1].cpu().numpy(), got.view(np.int32)]).T))
+    assert all((int(e[0, i]), int(e[1, i]), int(s[i:i + 1].view(np.int32)[0])) in pool_set for i in must[::37])
+    assert np.array_equal(got, s[got_pos_ok]) or np.array_equal(got, s[must])
