@@ -7,7 +7,7 @@ One STEP = the WHOLE filter job (/root/reference/filter.py:92-166) of the graph,
   GCN embeddings once (gcn_norm + L x [cuBLAS x·W row blocks + K1 SpMM]; row-sharded + all-gathered when N > 1)
   for every owner slab of the graph (all 576,289 owners, 8.26 G candidates on the ppa shape):
       K6+K3 fused, one pass : candidates + Adamic-Adar score of every candidate
-      K2 tcgen05            : GCN+LinkPredictor score of every candidate (bf16 prefilter)
+      K2 tcgen05            : GCN+LinkPredictor score of every candidate (fp16 operands: the prefilter)
       K4b + K4              : threshold push-down + running top-k (exact list for AA, tolerance band for GCN)
   fp32 re-scoring of the GCN band (K2 FFMA arm) -> the fp32 arm's exact top-k; one stable sort per list
   [N > 1: owners sharded by 2-path work, global k-th score exchanged, lists merged (NCCL)]
@@ -55,9 +55,9 @@ def parse():
     p.add_argument("--slab-pairs", type=int, default=1 << 27, help="candidate capacity of one owner slab")
     p.add_argument("--owners-frac", type=float, default=1.0,
                    help="score only the first fraction of the owners (debug / profiling runs; 1.0 = the whole graph)")
-    p.add_argument("--mlp", default=None, choices=[None, "prefilter", "fp32", "bf16"],
-                   help="K2 arm of the GCN filter: prefilter = tcgen05 bf16 scores + fp32 re-scoring of the band "
-                        "(default; the fp32 arm's exact list), bf16 = tensor-core scores only, fp32 = FFMA arm")
+    p.add_argument("--mlp", default=None, choices=[None, "prefilter", "fp32", "f16"],
+                   help="K2 arm of the GCN filter: prefilter = tcgen05 (fp16 operands) scores + fp32 re-scoring of the band "
+                        "(default; the fp32 arm's exact list), f16 = tensor-core scores only, fp32 = FFMA arm")
     p.add_argument("--scale", type=float, default=1.0, help="shrink the synthetic graph (debug only)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-extras", action="store_true",
@@ -97,11 +97,18 @@ def build_host_inputs(workload, scale=1.0):
         a = (6.0 / (ic + H)) ** 0.5
         sd[f"gnn.convs.{i}.weight"] = (torch.rand(ic, H, generator=g) * 2 - 1) * a
         sd[f"gnn.convs.{i}.bias"] = (torch.rand(H, generator=g) * 2 - 1) * 0.05
+    # LinkPredictor: random weights at the scale of a TRAINED filter model.  With nn.Linear's default init the
+    # pair-dependent signal (|h_u * h_v| ~ 1e-3 after three GCN layers) drowns in the hidden biases: every
+    # candidate of the graph scores 0.4869 +- 1e-4 (measured), the top-k boundary sits in a spike of ~4e9
+    # near-equal scores and neither a reduced-precision prefilter nor the ordering itself means anything.
+    # Hidden layers: He-uniform weights, zero biases (ReLU keeps the signal's scale); the output layer is
+    # rescaled on the device so that the logits have mean -2 and std 2 (``Workload.calibrate_model``), the
+    # score spread of a trained link predictor.  Work per candidate is unchanged.
     for i in range(L):
         oc = 1 if i == L - 1 else H
-        b = 1.0 / H ** 0.5
+        b = (6.0 / H) ** 0.5 if i < L - 1 else 1.0 / H ** 0.5
         sd[f"linkpred.lins.{i}.weight"] = (torch.rand(oc, H, generator=g) * 2 - 1) * b
-        sd[f"linkpred.lins.{i}.bias"] = (torch.rand(oc, generator=g) * 2 - 1) * b
+        sd[f"linkpred.lins.{i}.bias"] = torch.zeros(oc)
     host = dict(n=n, H=H, L=L, feat=feat, edge_index=torch.from_numpy(ei), workload=workload,
                 edge_weight=None if s["edge_weight"] is None else torch.from_numpy(np.concatenate([s["edge_weight"]] * 2)),
                 x=None if s["x"] is None else torch.from_numpy(s["x"]), sd=sd,
@@ -328,10 +335,32 @@ class Workload:
         self.model = models.build_model(margs, D, dev)        # parameter storage; every upload() refills it
         self.model.eval()
         self.copy_stream = torch.cuda.Stream(device=dev)
+        self.calibrate_model()
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in [self.h_rowptr, self.h_col] +
                              ([self.h_val] if self.h_val is not None else []) +
                              ([self.h_x] if self.h_x is not None else []) + list(self.h_sd.values()))
         self.owners = None if args.owners_frac >= 1.0 else (0, max(1, int(n * args.owners_frac)))
+
+    def calibrate_model(self):
+        """Rescale the output layer so that the fp32 logits of ~10^6 candidates have mean -2, std 2 (see
+        build_host_inputs).  Deterministic: same graph, same seeds, same sample on every rank."""
+        import torch
+        from edge_proposal_sets_b200 import candidates, ops
+        adj, x = self.upload()
+        h = self.model.embed(x, adj)
+        bounds = torch.cumsum(candidates.owner_bounds(adj), 0)
+        v_hi = int(torch.searchsorted(bounds, torch.tensor(1 << 20, device=self.dev)).item())
+        edges = candidates.two_hop(adj, 0, max(v_hi, 1))
+        lins = self.model.linkpred.lins
+        logit = ops.linkpred_mlp(h, edges, [l.weight for l in lins], [l.bias for l in lins], "fp32", sigmoid=False)
+        mean, std = float(logit.double().mean().item()), float(logit.double().std().item())
+        scale = 2.0 / max(std, 1e-30)
+        wl, bl = f"linkpred.lins.{self.L - 1}.weight", f"linkpred.lins.{self.L - 1}.bias"
+        self.h_sd[wl].mul_(scale)
+        self.h_sd[bl].copy_((self.h_sd[bl] - mean) * scale - 2.0)
+        self.host["sd"][wl], self.host["sd"][bl] = self.h_sd[wl].clone(), self.h_sd[bl].clone()
+        self.model_scale = dict(sample=int(edges.shape[1]), logit_mean_before=mean, logit_std_before=std, scale=scale)
+        self.model._h_key = None
 
     def upload(self):
         """H2D of everything the public call takes (graph first; features + weights on a copy stream)."""
@@ -478,7 +507,7 @@ def library_baseline(wl: Workload, adj, x, k):
         b_.record()
         torch.cuda.synchronize()
         out[f"torch_eager_{name}_mlp_pairs_per_s"] = nb * min(B, M) / (a.elapsed_time(b_) * 1e-3)
-    sc = model.linkpred.score_pairs(h, edges, "bf16")
+    sc = model.linkpred.score_pairs(h, edges, "f16")
     kk = min(k, M)
     for name, fn in (("torch_topk", lambda: torch.topk(sc, kk)), ("torch_sort_stable", lambda: torch.sort(sc, descending=True, stable=True))):
         fn()
@@ -496,8 +525,8 @@ def library_baseline(wl: Workload, adj, x, k):
     b_.record()
     torch.cuda.synchronize()
     out["eps_topk_k4_ms_per_slab"] = a.elapsed_time(b_)
-    for prec in ("bf16", "fp32"):
-        mm = M if prec == "bf16" else min(M, 1 << 23)
+    for prec in ("f16", "fp32"):
+        mm = M if prec == "f16" else min(M, 1 << 23)
         e_ = edges[:, :mm].contiguous()
         model.linkpred.score_pairs(h, e_, prec)
         a, b_ = ev(), ev()
@@ -653,9 +682,11 @@ def run_b200(args):
             "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": res["ms_step"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None,
-            "dtype": {"prefilter": "bf16 prefilter + f32 re-score (f32-exact lists)", "bf16": "bf16(mlp)/f32", "fp32": "f32"}[wl.mlp_arm],
-            "data": "synthetic",
-            "config": {"workload": workload_text(args.workload, k, args.slab_pairs),
+            "dtype": {"prefilter": "f16-operand tcgen05 prefilter (f32 accumulate) + f32 re-score: f32-exact lists", "f16": "f16(mlp operands)/f32",
+                      "fp32": "f32"}[wl.mlp_arm],
+            "data": "synthetic graph (seeded Chung-Lu of the named shape); seeded random weights, LinkPredictor at a "
+                    "trained model's score spread (He-uniform hidden layers, output layer rescaled to logit mean -2 / std 2)",
+            "config": {"workload": workload_text(args.workload, k, args.slab_pairs), "model_scale": wl.model_scale,
                        "n": n, "nnz": int(wl.h_col.numel()), "graph_total_candidates": int(res["total_pairs"]),
                        "candidates_rank0": int(M_rank), "slabs_rank0": slabs, "owners_rank0": st["owners"],
                        "owners_frac": args.owners_frac, "gnn": f"gcn L={L} H={H} F_in={H + wl.host['feat']}",

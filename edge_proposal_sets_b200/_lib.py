@@ -16,7 +16,8 @@ EPS_OK = 0
 EPS_VERSION = 200          # must equal EPS_VERSION in include/eps.h (checked by load())
 EPS_REDUCE_SUM, EPS_REDUCE_MEAN = 0, 1
 EPS_CN_SIGMOID, EPS_CN_GROUPED_BY_V = 1, 2
-EPS_MLP_FP32, EPS_MLP_TC_BF16 = 0, 1
+EPS_MLP_FP32, EPS_MLP_TC_F16 = 0, 1
+EPS_MLP_TC_BF16 = EPS_MLP_TC_F16       # round-1 name
 EPS_MLP_REUSE_WORKSPACE = 0x100
 EPS_CAND_SCORE_CN, EPS_CAND_SCORE_WSUM = 0, 1
 

@@ -53,13 +53,6 @@ int linkpred_tc_launch(const float *h, int n, int H, const int *pu, const int *p
                        size_t workspace_bytes, bool prepared, cudaStream_t stream);
 size_t linkpred_tc_workspace_bytes(int n, int H, int L, long long M);
 bool linkpred_tc_uses_table(int n, long long M);
-int linkpred_tc3_launch(const void *h, int h_is_bf16, int H, const int *pu, const int *pv, long long M,
-                        const MlpParams &prm, int L, int apply_sigmoid, float *score, uint8_t *img, int n,
-                        int *tile_order, cudaStream_t stream);
-int linkpred_tc2_launch(const float *h, const void *h_bf16, int H, const int *pu, const int *pv, long long M,
-                        const MlpParams &prm, int L, int apply_sigmoid, float *score, uint8_t *img, int n,
-                        int *tile_order, bool prepared, cudaStream_t stream);
-int h_to_bf16_launch(const float *h, long long elems, void *out, cudaStream_t stream);
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 

@@ -1,31 +1,1008 @@
 // K2 (tensor-core arm) — fused gather + Hadamard + LinkPredictor MLP on tcgen05 / TMEM.
 //
-// Replaces /root/reference/models.py:506 (two row gathers) + models.py:478-485 (LinkPredictor),
-// i.e. index_select x2, mul, (cuBLAS SGEMM + bias + relu) x (L-1), GEMV, sigmoid — 2L+3 launches
-// and 2*B*H*4 bytes of materialised gathers per batch in the reference.
+// Replaces /root/reference/models.py:506 (two row gathers) + models.py:478-485 (LinkPredictor), i.e.
+// index_select x2, mul, (cuBLAS SGEMM + bias + relu) x (L-1), GEMV, sigmoid — 2L+3 launches and 2*B*H*4 bytes of
+// materialised gathers per batch in the reference.  Operands are IEEE fp16 under a device-computed power-of-two
+// scale (tc_common.cuh), accumulation / output layer / sigmoid are fp32.
+// A cluster of two CTAs (tcgen05 cta_group::2) keeps its halves of ALL hidden-layer weights resident
+// in shared memory (with H = 256 one layer's fp16 weights are 128 KB: the pair splits the N dimension of the
+// B operand, 64 KB per SM and layer) and runs warp-specialised roles per CTA, connected by mbarriers:
 //
-// One CTA owns a tile of 128 candidate pairs (UMMA M = 128, cta_group::1):
-//   gather    h[u], h[v] rows (fp32, 128-bit loads), multiply in fp32, round to bf16 and store the
-//             A tile straight into shared memory in the UMMA canonical K-major SWIZZLE_128B layout;
-//   MMA       one elected thread issues tcgen05.mma.kind::f16 (bf16 x bf16 -> fp32) over K = H in
-//             steps of 16 against the layer's weight matrix, which sits in shared memory as a
-//             pre-swizzled bf16 image (packed once per call by pack_weights_kernel); the 128 x H
-//             fp32 accumulator lives in TMEM;
-//   epilogue  every thread owns one accumulator row (TMEM lane): tcgen05.ld 32 columns at a time,
-//             + bias, ReLU, then either bf16 -> shared memory as the next layer's A operand, or —
-//             for the last hidden layer — the H -> 1 output layer as a running dot product in
-//             registers, + bias, sigmoid, one coalesced 4-byte store per pair.
-// Arithmetic: bf16 operands, fp32 products/accumulation/bias/sigmoid.  Tolerance vs the fp32
-// reference path is stated in tests/test_gpu_mlp_tc.py and DESIGN.md.
+//   producers (8 warps)  gather h[u], h[v] from an fp16 copy of h (128-bit loads, the next chunk's
+//                        loads in flight while the current one is converted), multiply (HMUL2)
+//                        and fill a ring of 128 x 32 K-chunks (K-major SWIZZLE_64B, 4 stages at H = 256);
+//   MMA issuer (1 lane,  waits for a ring stage from BOTH CTAs, issues M=256 x N=H x K=16 UMMAs
+//   leader CTA only)     into one of two TMEM accumulator slots, releases stages / publishes
+//                        accumulators with multicast tcgen05.commit; later layers read their A operand
+//                        (the previous layer's activations) from a 3-slot ring of 64-column K-blocks;
+//   epilogue (4 warps)   thread-per-row: tcgen05.ld, + bias, ReLU, then either fp16 -> the activation
+//                        tile for the next layer — published per 64-column K-block, so the next
+//                        layer's MMAs start while the rest of the tile is still being converted —
+//                        or the fused H -> 1 output layer + sigmoid.
+//
+// The two accumulator slots let the tensor pipe start the next GEMM (next layer, or next tile's first
+// layer) while the epilogue drains the previous one; the ring decouples the HBM/L2 gather from both.
+#include <cooperative_groups.h>
+#include <stdio.h>
 #include <stdlib.h>
+
+#include <algorithm>
+#include <vector>
 
 #include "tc_common.cuh"
 
 namespace eps {
 
-// fp32 [out,in] weights of the hidden layers -> bf16 swizzled images, one H*H*2-byte image per layer
-__global__ void pack_weights_kernel(MlpParams prm, int H, int nhidden, uint8_t *img) {
-  const int chunks_per_row = H / 8;
+namespace cg = cooperative_groups;
+
+constexpr int P_MAX_RING = 8;                                      // first-layer ring stages (8 KB each), chosen at launch
+constexpr int P_A2_SLOTS = 3;                                      // activation K-block ring (16 KB each)
+constexpr int P_GROUP_WARPS = 4;                                   // warps per producer group
+// Warp roles: EW epilogue warps (4, or 8 = two per TMEM lane quarter, see the epilogue), then the MMA warp,
+// the pair-id warp and NG producer groups of four warps each.
+// one CTA per SM: the whole register file is there to be used
+// (16384 registers per SM sub-partition, warps dealt round-robin: 18 warps -> 5 on one -> 96; 14 -> 4 -> 128)
+constexpr int p_threads(int ng, int ew) { return (ew + 2 + ng * P_GROUP_WARPS) * 32; }
+constexpr int p_maxreg(int ng, int ew) { return (16384 / (((p_threads(ng, ew) / 32) + 3) / 4) / 32) / 8 * 8; }
+constexpr int P_CHUNK_K = 32;
+constexpr int P_STAGE_BYTES = TC_BM * P_CHUNK_K * 2;               // 8 KB
+
+__device__ __forceinline__ uint64_t umma_smem_desc_sw64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512u >> 4) << 32;                // 8 rows x 64 B
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                          // SWIZZLE_64B
+  return d;
+}
+// 16-wide K tiles (one UMMA K step, 32-byte rows) in K-major SWIZZLE_32B: 8-row groups 256 B apart,
+// 16-byte chunk index ^= bit 7 of the byte offset = (r >> 2) & 1
+__device__ __forceinline__ uint64_t umma_smem_desc_sw32(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256u >> 4) << 32;                // 8 rows x 32 B
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;                          // SWIZZLE_32B
+  return d;
+}
+__device__ __forceinline__ uint32_t sw32_chunk_off(int r, int chunk) {
+  return (uint32_t)r * 32u + (uint32_t)((chunk ^ ((r >> 2) & 1)) << 4);
+}
+// tcgen05.ld of 32 accumulator columns WITHOUT the wait, and a wait that names the destination
+// registers so no use of them can be scheduled above it: the epilogue keeps the next chunk's load in
+// flight while it converts the current one.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t *r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t *r) {
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;\n"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+        "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+        "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+        "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+      :: "memory");
+}
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t *r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t *r) {
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;\n"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+        "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+      :: "memory");
+}
+__device__ __forceinline__ uint32_t sw64_chunk_off(int r, int sub) {
+  return (uint32_t)r * 64u + (uint32_t)((sub ^ ((r >> 1) & 3)) << 4);
+}
+__device__ __forceinline__ void umma_f16_ss_2cta_p(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                                    uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}\n"
+      :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t mbar_saddr) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      :: "r"(mbar_saddr), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_on_cta(uint32_t local_saddr, uint32_t target_cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_saddr), "r"(target_cta));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(r) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t saddr, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t}\n"
+      :: "r"(saddr), "r"(parity) : "memory");
+}
+
+// Optional timeline trace of cluster 0 (build with -DEPS_TC3_TRACE; tools/tc3_trace.py reads the dump):
+// one record per pipeline event = tag | a | b | clock64 of the leader CTA's SM.
+#ifdef EPS_TC3_TRACE
+// fire-and-forget stores into a per-role region (MMA issuer 0, epilogue 1, producer group g 2+g); no atomics
+constexpr unsigned TR_REGION = 1u << 15;
+__device__ unsigned long long g_trace[8 * TR_REGION];
+#define TR_DECL(role) unsigned tr_n_ = 0; const unsigned tr_base_ = (unsigned)(role) * TR_REGION
+#define TR(tag, a, b)                                                                                  \
+  do {                                                                                                 \
+    if (cluster_id == 0 && cta_rank == 0 && tr_n_ < TR_REGION)                                         \
+      g_trace[tr_base_ + tr_n_++] = ((unsigned long long)(tag) << 56) | ((unsigned long long)((a) & 0xff) << 48) | \
+                      ((unsigned long long)((b) & 0xff) << 40) | ((unsigned long long)clock64() & 0xffffffffffull); \
+  } while (0)
+#else
+#define TR_DECL(role) do { } while (0)
+#define TR(tag, a, b) do { } while (0)
+#endif
+
+// one non-blocking look at a barrier phase (the blocking form may park the thread for a while)
+__device__ __forceinline__ uint32_t mbar_test(uint32_t saddr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}\n"
+      : "=r"(ok) : "r"(saddr), "r"(parity) : "memory");
+  return ok;
+}
+
+struct PipeBarriers {
+  uint64_t full[P_MAX_RING];   // producers (both CTAs) -> MMA issuer       (waited in the leader)
+  uint64_t empty[P_MAX_RING];  // MMA commit -> producers                    (multicast, both CTAs)
+  uint64_t acc_full[2];        // MMA commit -> epilogue                     (multicast, both CTAs)
+  uint64_t acc_free[2];        // epilogue (both CTAs) -> MMA issuer         (waited in the leader)
+  uint64_t a2_full[P_A2_SLOTS];   // epilogue (both CTAs) -> MMA issuer: a 64-column K-block of activations is in place
+  uint64_t a2_empty[P_A2_SLOTS];  // MMA commit -> epilogue                 (multicast, both CTAs)
+  uint64_t ids_full[2];        // ids warp -> producers                      (CTA-local)
+  uint64_t ids_empty[2];       // producers -> ids warp                      (CTA-local)
+  uint32_t tmem_base_slot;
+};
+
+__device__ __forceinline__ uint32_t cvt_relu_f16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));   // max(x, 0) then RN to fp16
+  return d;
+}
+__device__ __forceinline__ float2 add_f32x2(float2 a, float2 b) {   // FADD2: two fp32 adds, one issue slot
+  unsigned long long pa, pb, pr;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(pa) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(pb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(pr) : "l"(pa), "l"(pb));
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(pr));
+  return r;
+}
+__device__ __forceinline__ float2 fma_f32x2(float2 a, float2 b, float2 c) {
+  unsigned long long pa, pb, pc, pr;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(pa) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(pb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(pc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(pr) : "l"(pa), "l"(pb), "l"(pc));
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(pr));
+  return r;
+}
+
+template <int H, bool HB /* h is the fp16 table (else fp32) */, int NG /* producer groups */, int EW /* epilogue warps */>
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(p_maxreg(NG, EW))
+linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, const int *__restrict__ pv,
+                    long long M, const MlpParams prm, int L, int apply_sigmoid,
+                    const uint8_t *__restrict__ wimg, float *__restrict__ score, int tune, int ring,
+                    const int *__restrict__ tile_order, const TcScale *__restrict__ scale) {
+  static_assert(H % 64 == 0 && H >= 64 && H <= 256, "H in {64,128,192,256}");
+  constexpr int HH = H / 2;
+  constexpr int WH_BYTES = HH * H * 2;
+  constexpr int A2_SLOT_BYTES = TC_BM * 128;                  // 128 rows x 64 K fp16, SWIZZLE_128B
+  constexpr int NCHUNK = H / P_CHUNK_K;
+  constexpr int NKB = H / 64;
+  constexpr int P_EPI_WARPS = EW;
+  constexpr int P_IDS_WARP = EW + 1, P_FIRST_PROD_WARP = EW + 2;
+  constexpr int P_THREADS = p_threads(NG, EW);
+  constexpr int P_PROD_WARPS = NG * P_GROUP_WARPS;
+  constexpr uint32_t TMEM_COLS = 2 * H <= 128 ? 128 : (2 * H <= 256 ? 256 : 512);
+  constexpr uint32_t IDESC = umma_idesc_f16(2 * TC_BM, H);
+  // ALL shared memory is dynamic and laid out by hand (no alignment pad: the window itself is 1 KB
+  // aligned — checked below — and every swizzled region starts at a multiple of 1 KB).  With H = 256
+  // and two hidden layers the resident weights take 128 KB; the rest is two rings: `ring` stages of
+  // the first layer's A operand (8 KB each, as many as fit) and P_A2_SLOTS K-blocks of activations.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int nhidden = L - 1;
+  uint8_t *sW = smem;                                                   // [nhidden][WH_BYTES]
+  uint8_t *sRing = sW + (size_t)nhidden * WH_BYTES;                     // [ring][8 KB]
+  uint8_t *sA2 = sRing + (size_t)ring * P_STAGE_BYTES;                  // [P_A2_SLOTS][16 KB] (nhidden >= 2)
+  uint8_t *sOnes = sA2 + (nhidden >= 2 ? P_A2_SLOTS * A2_SLOT_BYTES : 0);   // [128][16] fp16: A of the bias K-step
+  uint8_t *sBiasB = sOnes + TC_BM * 32;                                 // [nhidden][HH][16] fp16: B of the bias K-step
+  float *sWlast = reinterpret_cast<float *>(sBiasB + (size_t)nhidden * HH * 32);   // [H]
+  int2 *sIds = reinterpret_cast<int2 *>(sWlast + H);                    // [2][128] (u, v) of this CTA's rows
+  float *sPart = reinterpret_cast<float *>(sIds + 2 * TC_BM);           // [2][128] output-layer partial sums (EW = 8)
+  PipeBarriers &bars = *reinterpret_cast<PipeBarriers *>(sPart + 2 * TC_BM);
+  cg::cluster_group cluster = cg::this_cluster();
+  const uint32_t cta_rank = cluster.block_rank();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  const float hscale = scale->hscale, S = scale->S, invS = scale->invS;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"(smem_u32(&bars.tmem_base_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int i = 0; i < P_MAX_RING; ++i) {
+      mbar_init(smem_u32(&bars.full[i]), 2 * P_GROUP_WARPS);
+      mbar_init(smem_u32(&bars.empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bars.acc_full[i]), 1);
+      mbar_init(smem_u32(&bars.acc_free[i]), 2 * P_EPI_WARPS);
+    }
+    for (int i = 0; i < P_A2_SLOTS; ++i) {
+      mbar_init(smem_u32(&bars.a2_full[i]), 2 * P_EPI_WARPS);
+      mbar_init(smem_u32(&bars.a2_empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bars.ids_full[i]), 1);
+      mbar_init(smem_u32(&bars.ids_empty[i]), P_PROD_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int l = 0; l < nhidden; ++l) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(wimg + (size_t)l * H * H * 2 + (size_t)cta_rank * WH_BYTES);
+    uint4 *dst = reinterpret_cast<uint4 *>(sW + (size_t)l * WH_BYTES);
+    for (int i = tid; i < WH_BYTES / 16; i += P_THREADS) dst[i] = __ldg(src + i);
+  }
+  // Biases ride in the MMA: one extra K = 16 step per hidden layer with A = [1 1 1 0 ...] for every
+  // row and B[n] = [hi mid lo 0 ...], S times the bias of output feature n split into three fp16 terms
+  // (hi + mid + lo reproduces the fp32 value exactly: 3 x 11 significand bits).  The epilogue then never touches shared
+  // memory for a bias, and the accumulator is initialised by this step instead of a zeroing MMA flag.
+  for (int i = tid; i < TC_BM; i += P_THREADS) {
+    const uint32_t one2 = 0x3C003C00u;                               // fp16 (1, 1)
+    *reinterpret_cast<uint4 *>(sOnes + sw32_chunk_off(i, 0)) = make_uint4(one2, 0x00003C00u, 0u, 0u);
+    *reinterpret_cast<uint4 *>(sOnes + sw32_chunk_off(i, 1)) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  for (int i = tid; i < nhidden * HH; i += P_THREADS) {
+    const int l = i / HH, r = i - l * HH;
+    const float b = __ldg(prm.b[l] + cta_rank * HH + r) * S;     // hidden activations are carried times S
+    const __half hi = __float2half_rn(b);
+    const float r1 = b - __half2float(hi);
+    const __half mid = __float2half_rn(r1);
+    const __half lo = __float2half_rn(r1 - __half2float(mid));
+    const uint32_t w0 = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(mid) << 16);
+    uint8_t *t = sBiasB + (size_t)l * HH * 32;
+    *reinterpret_cast<uint4 *>(t + sw32_chunk_off(r, 0)) = make_uint4(w0, (uint32_t)__half_as_ushort(lo), 0u, 0u);
+    *reinterpret_cast<uint4 *>(t + sw32_chunk_off(r, 1)) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  for (int i = tid; i < H; i += P_THREADS) sWlast[i] = __ldg(prm.W[L - 1] + i) * invS;   // exact: S is a power of two
+  const float b_last = __ldg(prm.b[L - 1]);
+  fence_async_smem();
+  tc_fence_before();
+  cluster.sync();
+  tc_fence_after();
+  const uint32_t tmem_base = bars.tmem_base_slot;
+
+  const long long npair_tiles = (M + 2 * TC_BM - 1) / (2 * TC_BM);
+  const long long nclusters = gridDim.x / 2, cluster_id = blockIdx.x / 2;
+  const int G = (tune & 2) ? 2 : 1;       // tiles per issue group (see the MMA issuer)
+
+  if (warp < P_EPI_WARPS) {
+   if constexpr (EW == 8) {
+    // =============================== EPILOGUE, two warps per TMEM lane quarter ===============================
+    // Draining a 128 x H fp32 accumulator through tcgen05.ld costs about as long as the GEMM that filled it,
+    // and the next layer's MMAs wait for its K-blocks: with one warp per lane quarter a 64-column K-block took
+    // ~790 clocks against 512 for the MMAs that consume it (profiles/round1_c_tc3_timeline.md).  Here warps q
+    // and q + 4 share the rows of quarter q and split every K-block's columns (32 each), so a quarter always has
+    // a tcgen05.ld in flight while the other warp converts.  Hidden layers: cvt.rn.relu.f16x2 + swizzled
+    // 128-bit stores (the bias is already in the accumulator); output layer: each warp dots its 128 columns,
+    // the halves meet in shared memory (one 64-thread named barrier per quarter).
+    constexpr int NL = 2 * NKB;                     // 16-column loads per warp and accumulator
+    TR_DECL(1);
+    uint32_t acph = 0, a2g = 0, seq = 0, fin = 0;
+    const int q = warp & 3, hf = warp >> 2;
+    const int row = q * 32 + lane;
+    for (long long tile0 = cluster_id; tile0 < npair_tiles; tile0 += G * nclusters) {
+      const int nj = (G == 2 && tile0 + nclusters < npair_tiles) ? 2 : 1;
+      for (int l = 0; l < nhidden; ++l)
+      for (int tj = 0; tj < nj; ++tj) {
+        const long long sched = tile0 + tj * nclusters;
+        const long long p0 = (tile_order ? (long long)__ldg(tile_order + sched) : sched) * (2 * TC_BM) +
+                             (long long)cta_rank * TC_BM;
+        const uint32_t slot = G == 2 ? (uint32_t)tj : (seq++ & 1u);
+        mbar_wait_cluster(smem_u32(&bars.acc_full[slot]), (acph >> slot) & 1u);
+        acph ^= 1u << slot;
+        tc_fence_after();
+        if (tid == 0) TR(5, l, tj);
+        // this warp's columns of the accumulator: 64 kb + 32 hf + [0, 32), kb < NKB, as NL loads of 16
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * H + (uint32_t)hf * 32u;
+        uint32_t buf[2][16];
+        tmem_ld16_issue(taddr, buf[0]);
+        if (l < nhidden - 1) {
+          uint4 hold[4];
+#pragma unroll
+          for (int kb = 0; kb < NKB; ++kb) {
+            const bool last_kb = kb == NKB - 1;       // held in registers: see the one-warp-per-quarter path below
+            uint8_t *dstrow = nullptr;
+            uint32_t a2s = 0;
+            if (!last_kb) {
+              a2s = a2g % P_A2_SLOTS;
+              mbar_wait_cluster(smem_u32(&bars.a2_empty[a2s]), ((a2g / P_A2_SLOTS) & 1u) ^ 1u);
+              dstrow = sA2 + a2s * A2_SLOT_BYTES + row * 128;
+            }
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int li = kb * 2 + half;
+              tmem_ld_wait16(buf[li & 1]);
+              if (li + 1 < NL)
+                tmem_ld16_issue(taddr + (uint32_t)(((li + 1) >> 1) * 64 + ((li + 1) & 1) * 16), buf[(li + 1) & 1]);
+              const uint32_t *v = buf[li & 1];
+#pragma unroll
+              for (int j = 0; j < 16; j += 8) {
+                uint4 o;
+                o.x = cvt_relu_f16x2(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
+                o.y = cvt_relu_f16x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                o.z = cvt_relu_f16x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+                o.w = cvt_relu_f16x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+                const int sub = half * 2 + (j >> 3);               // 16-byte unit inside this warp's 64 bytes
+                if (last_kb) hold[sub] = o;
+                else *reinterpret_cast<uint4 *>(dstrow + (((hf * 4 + sub) ^ (row & 7)) << 4)) = o;
+              }
+            }
+            if (!last_kb) {
+              fence_async_smem();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.a2_full[a2s]), 0);
+              if (tid == 0) TR(6, kb, tj);
+              ++a2g;
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.acc_free[slot]), 0);
+          if (tid == 0) TR(7, l, tj);
+          const uint32_t a2s = a2g % P_A2_SLOTS;
+          mbar_wait_cluster(smem_u32(&bars.a2_empty[a2s]), ((a2g / P_A2_SLOTS) & 1u) ^ 1u);
+          uint8_t *dstrow = sA2 + a2s * A2_SLOT_BYTES + row * 128;
+#pragma unroll
+          for (int sub = 0; sub < 4; ++sub)
+            *reinterpret_cast<uint4 *>(dstrow + (((hf * 4 + sub) ^ (row & 7)) << 4)) = hold[sub];
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.a2_full[a2s]), 0);
+          if (tid == 0) TR(6, NKB - 1, tj);
+          ++a2g;
+        } else {
+          const float4 *w4 = reinterpret_cast<const float4 *>(sWlast);
+          float2 part = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int li = 0; li < NL; ++li) {
+            tmem_ld_wait16(buf[li & 1]);
+            if (li + 1 < NL)
+              tmem_ld16_issue(taddr + (uint32_t)(((li + 1) >> 1) * 64 + ((li + 1) & 1) * 16), buf[(li + 1) & 1]);
+            const uint32_t *v = buf[li & 1];
+            const int cbase = (li >> 1) * 64 + hf * 32 + (li & 1) * 16;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 wa = w4[(cbase + j) >> 2];
+              float2 t0 = make_float2(fmaxf(__uint_as_float(v[j + 0]), 0.f), fmaxf(__uint_as_float(v[j + 1]), 0.f));
+              float2 t1 = make_float2(fmaxf(__uint_as_float(v[j + 2]), 0.f), fmaxf(__uint_as_float(v[j + 3]), 0.f));
+              part = fma_f32x2(t0, make_float2(wa.x, wa.y), part);
+              part = fma_f32x2(t1, make_float2(wa.z, wa.w), part);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.acc_free[slot]), 0);
+          if (tid == 0) TR(7, l, tj);
+          // the two column halves of a row meet in shared memory; the buffer alternates per output tile, and the
+          // barrier of the NEXT tile orders this tile's read before the write that reuses the buffer
+          float *sp = sPart + (fin & 1u) * TC_BM;
+          const float mine = part.x + part.y;
+          if (hf == 1) sp[row] = mine;
+          asm volatile("bar.sync %0, 64;" :: "r"(1 + q) : "memory");
+          if (hf == 0 && p0 + row < M) {
+            const float sc = (mine + sp[row]) + b_last;
+            score[p0 + row] = apply_sigmoid ? sigmoidf_ref(sc) : sc;
+          }
+          ++fin;
+        }
+      }
+    }
+   } else {
+    // =============================== EPILOGUE ===============================
+    // Thread-per-row.  The accumulator already holds W x + b (the bias K-step), so a hidden-layer
+    // element costs one half of a cvt.rn.relu.f16x2 and an eighth of a 128-bit shared store — no
+    // shared-memory reads at all; the output layer reads its H weights with warp-uniform 128-bit
+    // loads.  The next 32 columns are always in flight (tcgen05.ld) while the current 32 are converted.
+    constexpr int NCH = H / 32;
+    TR_DECL(1);
+    uint32_t acph = 0;            // bit s = phase parity of acc_full[s] (kept in a register)
+    uint32_t a2g = 0;             // a2g: activation K-blocks produced so far (slot = a2g % P_A2_SLOTS)
+    const int row = warp * 32 + lane;
+    // Same tile / layer / slot order as the MMA issuer (see there).
+    uint32_t seq = 0;
+    for (long long tile0 = cluster_id; tile0 < npair_tiles; tile0 += G * nclusters) {
+      const int nj = (G == 2 && tile0 + nclusters < npair_tiles) ? 2 : 1;
+      for (int l = 0; l < nhidden; ++l)
+      for (int tj = 0; tj < nj; ++tj) {
+        const long long sched = tile0 + tj * nclusters;       // schedule slot -> pair tile (u-block order)
+        const long long p0 = (tile_order ? (long long)__ldg(tile_order + sched) : sched) * (2 * TC_BM) +
+                             (long long)cta_rank * TC_BM;
+        const uint32_t slot = G == 2 ? (uint32_t)tj : (seq++ & 1u);
+        mbar_wait_cluster(smem_u32(&bars.acc_full[slot]), (acph >> slot) & 1u);
+        acph ^= 1u << slot;
+        tc_fence_after();
+        if (tid == 0) TR(5, l, tj);
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + slot * H;
+        uint32_t buf[2][32];
+        tmem_ld32_issue(taddr, buf[0]);
+        if (l < nhidden - 1) {
+          // The LAST K-block of the tile is converted into registers, not stored: the accumulator slot
+          // is handed back (acc_free) as soon as every column has been read, and only then does the
+          // warp wait for a free slot of the activation ring.  The ring holds fewer K-blocks than a
+          // tile has, and the MMAs that drain it (the next layer of THIS tile) write the very slot
+          // being read here — so they must not be a precondition for finishing the read.
+          uint8_t *dstrow = nullptr;
+          uint32_t a2s = 0;
+          uint4 hold[8];
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            tmem_ld_wait(buf[c & 1]);
+            if (c + 1 < NCH) tmem_ld32_issue(taddr + (uint32_t)(c + 1) * 32u, buf[(c + 1) & 1]);
+            const bool last_kb = c >= NCH - 2;
+            if (!last_kb && (c & 1) == 0) {
+              // K-block c/2 of the next layer's A operand goes to slot a2g % 3 of the activation ring:
+              // wait until the MMAs that read the slot's previous contents have retired
+              a2s = a2g % P_A2_SLOTS;
+              mbar_wait_cluster(smem_u32(&bars.a2_empty[a2s]), ((a2g / P_A2_SLOTS) & 1u) ^ 1u);
+              dstrow = sA2 + a2s * A2_SLOT_BYTES + row * 128;
+            }
+            const uint32_t *v = buf[c & 1];
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 o;
+              o.x = cvt_relu_f16x2(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
+              o.y = cvt_relu_f16x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              o.z = cvt_relu_f16x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+              o.w = cvt_relu_f16x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+              const int chunk = (c & 1) * 4 + (j >> 3);
+              if (last_kb) hold[chunk] = o;
+              else *reinterpret_cast<uint4 *>(dstrow + ((chunk ^ (row & 7)) << 4)) = o;
+            }
+            if (!last_kb && (c & 1)) {
+              // the K-block is complete: the tensor pipe starts the next layer on it while the
+              // remaining columns of this tile are still being converted
+              fence_async_smem();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.a2_full[a2s]), 0);
+              if (tid == 0) TR(6, c >> 1, tj);
+              ++a2g;
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.acc_free[slot]), 0);
+          if (tid == 0) TR(7, l, tj);
+          a2s = a2g % P_A2_SLOTS;
+          mbar_wait_cluster(smem_u32(&bars.a2_empty[a2s]), ((a2g / P_A2_SLOTS) & 1u) ^ 1u);
+          dstrow = sA2 + a2s * A2_SLOT_BYTES + row * 128;
+#pragma unroll
+          for (int chunk = 0; chunk < 8; ++chunk)
+            *reinterpret_cast<uint4 *>(dstrow + ((chunk ^ (row & 7)) << 4)) = hold[chunk];
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.a2_full[a2s]), 0);
+          if (tid == 0) TR(6, NKB - 1, tj);
+          ++a2g;
+        } else {
+          const float4 *w4 = reinterpret_cast<const float4 *>(sWlast);
+          float2 part = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            tmem_ld_wait(buf[c & 1]);
+            if (c + 1 < NCH) tmem_ld32_issue(taddr + (uint32_t)(c + 1) * 32u, buf[(c + 1) & 1]);
+            const uint32_t *v = buf[c & 1];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 wa = w4[(c * 32 + j) >> 2];
+              float2 t0 = make_float2(fmaxf(__uint_as_float(v[j + 0]), 0.f), fmaxf(__uint_as_float(v[j + 1]), 0.f));
+              float2 t1 = make_float2(fmaxf(__uint_as_float(v[j + 2]), 0.f), fmaxf(__uint_as_float(v[j + 3]), 0.f));
+              part = fma_f32x2(t0, make_float2(wa.x, wa.y), part);
+              part = fma_f32x2(t1, make_float2(wa.z, wa.w), part);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.acc_free[slot]), 0);
+          if (tid == 0) TR(7, l, tj);
+          if (p0 + row < M) {
+            const float s = (part.x + part.y) + b_last;
+            score[p0 + row] = apply_sigmoid ? sigmoidf_ref(s) : s;
+          }
+        }
+      }
+    }
+   }
+  } else if (warp == P_EPI_WARPS) {
+    // =============================== MMA ISSUER (leader CTA, one lane) ===============================
+    if (cta_rank == 0 && lane == 0) {   // lanes 1..31 wait at the __syncwarp below (keeps the warp
+                                        // converged for the aligned cluster barrier at the end)
+      TR_DECL(0);
+      // This one thread is the tensor pipe's instruction stream: whatever it executes between two
+      // tcgen05.mma is time the pipe idles once its short queue drains.  So nothing is derived per
+      // iteration — descriptors are a precomputed 64-bit base plus a small constant (the start-address
+      // field counts 16-byte units and never carries out of its 14 bits), ring positions and barrier
+      // phases are carried incrementally (no division by the run-time ring depth).
+      uint32_t afph = 0;
+      const uint64_t dRing = umma_smem_desc_sw64(smem_u32(sRing)), dA2 = umma_smem_desc(smem_u32(sA2));
+      const uint64_t dW = umma_smem_desc(smem_u32(sW));
+      const uint64_t dOnes = umma_smem_desc_sw32(smem_u32(sOnes)), dBias = umma_smem_desc_sw32(smem_u32(sBiasB));
+      const uint32_t full0 = smem_u32(&bars.full[0]), empty0 = smem_u32(&bars.empty[0]);
+      const uint32_t a2full0 = smem_u32(&bars.a2_full[0]), a2empty0 = smem_u32(&bars.a2_empty[0]);
+      uint32_t stage = 0, stage_ph = 0;        // first-layer ring position / parity of full[stage]
+      uint32_t a2s = 0, a2_ph = 0;             // activation ring position / parity of a2_full[a2s]
+      // Issue order.  G = 1: tile by tile, the layers of a tile alternate between the two accumulator
+      // slots (layer l+1 trails the epilogue of layer l K-block by K-block, the next tile's first
+      // layer overlaps the last epilogue).  G = 2 (tune bit 1): layer by layer over a PAIR of tiles,
+      // tile j in slot j, so every dependent step has a whole GEMM of the other tile to hide behind —
+      // at the price of first-layer bursts twice as long for the gather ring to absorb.
+      uint32_t seq = 0;
+      for (long long tile0 = cluster_id; tile0 < npair_tiles; tile0 += G * nclusters) {
+        const int nj = (G == 2 && tile0 + nclusters < npair_tiles) ? 2 : 1;
+        for (int l = 0; l < nhidden; ++l)
+        for (int tj = 0; tj < nj; ++tj) {
+          const uint32_t slot = G == 2 ? (uint32_t)tj : (seq++ & 1u);
+          mbar_wait_cluster(smem_u32(&bars.acc_free[slot]), ((afph >> slot) & 1u) ^ 1u);   // first use passes
+          afph ^= 1u << slot;
+          tc_fence_after();
+          TR(1, l, tj);
+          const uint32_t d = tmem_base + slot * H;
+          // bias K-step: initialises the accumulator with b[l] in every row
+          umma_f16_ss_2cta_p(d, dOnes, dBias + (uint64_t)(l * ((HH * 32) >> 4)), IDESC, 0u);
+          const uint64_t dWl = dW + (uint64_t)(l * (WH_BYTES >> 4));
+          // The barrier of the NEXT stage / K-block is looked at right after the first MMA of the current
+          // one has been issued, so its round trip to shared memory runs under that MMA instead of
+          // between two of them.
+          if (l == 0) {
+            uint32_t ready = 0;
+#pragma unroll
+            for (int c = 0; c < NCHUNK; ++c) {
+              if (!ready) mbar_wait_cluster(full0 + stage * 8u, stage_ph);
+              tc_fence_after();
+              TR(2, c, tj);
+              const uint64_t ad = dRing + (uint64_t)(stage * (P_STAGE_BYTES >> 4));
+              const uint32_t cur = stage;
+              if (++stage == (uint32_t)ring) { stage = 0; stage_ph ^= 1u; }
+#pragma unroll
+              for (int k16 = 0; k16 < P_CHUNK_K / 16; ++k16) {
+                const int k = c * P_CHUNK_K + k16 * 16;
+                umma_f16_ss_2cta_p(d, ad + (uint64_t)(k16 * 2),
+                                    dWl + (uint64_t)(((k >> 6) * (HH * 128) + ((k & 63) >> 4) * 32) >> 4), IDESC, 1u);
+                if (k16 == 0) ready = (c + 1 < NCHUNK) ? mbar_test(full0 + stage * 8u, stage_ph) : 0u;
+              }
+              umma_commit_mc(empty0 + cur * 8u);
+            }
+          } else {
+            uint32_t ready = 0;
+#pragma unroll
+            for (int kb = 0; kb < NKB; ++kb) {
+              if (!ready) mbar_wait_cluster(a2full0 + a2s * 8u, a2_ph);   // K-block kb is in place
+              tc_fence_after();
+              TR(3, kb, tj);
+              const uint64_t ad = dA2 + (uint64_t)(a2s * (A2_SLOT_BYTES >> 4));
+              const uint32_t cur = a2s;
+              if (++a2s == P_A2_SLOTS) { a2s = 0; a2_ph ^= 1u; }
+#pragma unroll
+              for (int k16 = 0; k16 < 4; ++k16) {
+                umma_f16_ss_2cta_p(d, ad + (uint64_t)(k16 * 2), dWl + (uint64_t)((kb * (HH * 128) + k16 * 32) >> 4), IDESC, 1u);
+                if (k16 == 2) ready = (kb + 1 < NKB) ? mbar_test(a2full0 + a2s * 8u, a2_ph) : 0u;
+              }
+              umma_commit_mc(a2empty0 + cur * 8u);      // slot reusable once these MMAs retire
+            }
+          }
+          umma_commit_mc(smem_u32(&bars.acc_full[slot]));
+          TR(4, l, tj);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == P_IDS_WARP) {
+    // =============================== PAIR-ID PREFETCH ===============================
+    // one tile ahead of the producers: (u, v) of this CTA's 128 rows -> shared memory, so the row
+    // gathers never wait on a dependent index load
+    long long tl = 0;
+    for (long long tile = cluster_id; tile < npair_tiles; tile += nclusters, ++tl) {
+      const int slot = (int)(tl & 1);
+      mbar_wait_cluster(smem_u32(&bars.ids_empty[slot]), (uint32_t)(((tl >> 1) & 1) ^ 1));
+      const long long p0 = (tile_order ? (long long)__ldg(tile_order + tile) : tile) * (2 * TC_BM) +
+                           (long long)cta_rank * TC_BM;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = lane + 32 * q;
+        int2 id = make_int2(-1, -1);
+        if (p0 + r < M) { id.x = __ldg(pu + p0 + r); id.y = __ldg(pv + p0 + r); }
+        sIds[slot * TC_BM + r] = id;
+        // pull the whole embedding rows of the NEXT tile into L2 now (one DRAM page visit per row
+        // instead of eight chunk-sized ones later); the producers' loads then hit L2
+        const int vprev = __shfl_up_sync(FULL, id.y, 1);
+        if ((tune & 1) && id.x >= 0) {
+          constexpr int RB = H * (HB ? 2 : 4);
+          const char *ru = reinterpret_cast<const char *>(h) + (size_t)id.x * RB;
+#pragma unroll
+          for (int b = 0; b < RB; b += 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(ru + b));
+          if (lane == 0 || vprev != id.y) {                  // runs of equal v: prefetch each row once
+            const char *rv = reinterpret_cast<const char *>(h) + (size_t)id.y * RB;
+#pragma unroll
+            for (int b = 0; b < RB; b += 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(rv + b));
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.ids_full[slot]), cta_rank);
+    }
+  } else {
+    // =============================== PRODUCERS ===============================
+    // Three independent groups of four warps; group g produces chunks g, g+3, g+6, ... of the
+    // flattened chunk stream of this CTA's tiles (a chunk = 128 rows x 32 K) into ring stage
+    // (chunk % ring) — more stages than groups, so a group never waits on the stage it has just filled.
+    // Lane mapping inside a group (128 threads): 4 consecutive lanes cover one row's chunk, each lane
+    // 8 K-elements = one 16-byte unit of the swizzled stage; a warp instruction covers 8 rows, and
+    // rows that share v (the common case inside a run of the column-major candidate order) coalesce
+    // into one request.
+    //   HB (fp16 copy of h, the hot path): 2 x LDG.128 per row (u, v) -> 8 loads per chunk, and the
+    //       loads of the NEXT chunk are issued before the current one is converted (two register
+    //       buffers), so every producer thread keeps 8-16 x 16 B in flight (~75 KB per SM);
+    //   fp32 source (small pair lists, no table): 4 x LDG.128 per row, one chunk in flight.
+    const int pw = warp - P_FIRST_PROD_WARP;                 // 0..11
+    const int group = pw / P_GROUP_WARPS;
+    const int t = (pw % P_GROUP_WARPS) * 32 + lane;          // 0..127
+    const int l4 = t & 3;
+    const int rg = t >> 2;                                   // 0..31 ; rows rg + 32 q, q < 4
+    long long my_tiles = 0;
+    if (cluster_id < npair_tiles) my_tiles = (npair_tiles - cluster_id + nclusters - 1) / nclusters;
+    const long long total = my_tiles * NCHUNK;
+    const char *hbase = reinterpret_cast<const char *>(h);
+    constexpr int ROW_BYTES = H * (HB ? 2 : 4);
+    constexpr int LPR = HB ? 1 : 2;                          // LDG.128 per row and operand
+    long long cur_tl = -1;
+    int idu[4], idv[4];
+    TR_DECL(2 + group);
+    // h[v] is loaded ONCE per thread and chunk: the candidate list is grouped by v (runs of thousands
+    // of pairs), so a thread's four rows almost always share it.  A row whose v differs (a run boundary,
+    // or an arbitrary pair list) fetches its own copy when the buffer is consumed.  Besides a quarter of
+    // the L1 wavefronts this frees 12 registers per buffer, which is what lets two buffers live in the
+    // 96 registers a 576-thread CTA can have.
+    struct Buf { uint4 xu[4][LPR], xv[LPR]; int v[4]; uint32_t valid; };
+
+    // Move this warp's position in the pair-id pipeline to tile `tl`: release every tile left behind
+    // (also tiles this group has no chunk in — H = 64 has 2 chunks per tile for 3 groups), waiting
+    // for each tile's ids to have been published first so that a release can never be counted
+    // towards an earlier phase of the same slot.
+    auto advance_to = [&](long long tl) {
+      while (cur_tl < tl) {
+        if (cur_tl >= 0) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.ids_empty[cur_tl & 1]), cta_rank);
+        }
+        ++cur_tl;
+        if (cur_tl < my_tiles)
+          mbar_wait_cluster(smem_u32(&bars.ids_full[cur_tl & 1]), (uint32_t)((cur_tl >> 1) & 1));
+      }
+    };
+    auto issue = [&](Buf &b, long long i) {
+      const long long tl = i / NCHUNK;
+      const int c = (int)(i - tl * NCHUNK);
+      if (tl != cur_tl) {
+        advance_to(tl);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int2 id = sIds[(tl & 1) * TC_BM + rg + 32 * q];
+          idu[q] = id.x; idv[q] = id.y;
+        }
+      }
+      const int boff = (c * P_CHUNK_K + l4 * 8) * (HB ? 2 : 4);
+      if (t == 0) TR(8, c, group);
+      b.valid = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        b.v[q] = idv[q];
+        if (idu[q] >= 0) {
+          b.valid |= 1u << q;
+          const uint4 *pu4 = reinterpret_cast<const uint4 *>(hbase + (size_t)idu[q] * ROW_BYTES + boff);
+#pragma unroll
+          for (int j = 0; j < LPR; ++j) b.xu[q][j] = __ldg(pu4 + j);
+        }
+      }
+      if (b.valid) {                                         // rows are valid from q = 0 up
+        const uint4 *pv4 = reinterpret_cast<const uint4 *>(hbase + (size_t)idv[0] * ROW_BYTES + boff);
+#pragma unroll
+        for (int j = 0; j < LPR; ++j) b.xv[j] = __ldg(pv4 + j);
+      }
+    };
+    // ring position of this group's next chunk and the parity its `empty` barrier is waited with,
+    // carried incrementally (the group's chunks are NG apart and NG < ring: at most one wrap a step)
+    uint32_t pstage = (uint32_t)group, pphase = 1u;
+    auto consume = [&](Buf &b, long long i) {
+      const uint32_t stage = pstage;
+      uint8_t *dst = sRing + stage * P_STAGE_BYTES;
+      const int boff = ((int)(i % NCHUNK) * P_CHUNK_K + l4 * 8) * (HB ? 2 : 4);
+      mbar_wait_cluster(smem_u32(&bars.empty[stage]), pphase);   // the MMAs that read this stage retired
+      pstage += NG;
+      if (pstage >= (uint32_t)ring) { pstage -= (uint32_t)ring; pphase ^= 1u; }
+      if (t == 0) TR(9, (int)(i % NCHUNK), group);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = rg + 32 * q;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if ((b.valid >> q) & 1u) {
+          uint4 xv[LPR];
+#pragma unroll
+          for (int j = 0; j < LPR; ++j) xv[j] = b.xv[j];
+          if (q > 0 && b.v[q] != b.v[0]) {
+            const uint4 *pv4 = reinterpret_cast<const uint4 *>(hbase + (size_t)b.v[q] * ROW_BYTES + boff);
+#pragma unroll
+            for (int j = 0; j < LPR; ++j) xv[j] = __ldg(pv4 + j);
+          }
+          if (HB) {
+            o.x = mul_f16x2(b.xu[q][0].x, xv[0].x); o.y = mul_f16x2(b.xu[q][0].y, xv[0].y);
+            o.z = mul_f16x2(b.xu[q][0].z, xv[0].z); o.w = mul_f16x2(b.xu[q][0].w, xv[0].w);
+          } else {
+            const uint4 a0 = b.xu[q][0], a1 = b.xu[q][LPR - 1], c0 = xv[0], c1 = xv[LPR - 1];
+            o.x = hadamard_f16x2(__uint_as_float(a0.x), __uint_as_float(a0.y), __uint_as_float(c0.x), __uint_as_float(c0.y), hscale);
+            o.y = hadamard_f16x2(__uint_as_float(a0.z), __uint_as_float(a0.w), __uint_as_float(c0.z), __uint_as_float(c0.w), hscale);
+            o.z = hadamard_f16x2(__uint_as_float(a1.x), __uint_as_float(a1.y), __uint_as_float(c1.x), __uint_as_float(c1.y), hscale);
+            o.w = hadamard_f16x2(__uint_as_float(a1.z), __uint_as_float(a1.w), __uint_as_float(c1.z), __uint_as_float(c1.w), hscale);
+          }
+        }
+        *reinterpret_cast<uint4 *>(dst + sw64_chunk_off(r, l4)) = o;
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.full[stage]), 0);
+      if (t == 0) TR(10, (int)(i % NCHUNK), group);
+    };
+
+    long long i = group;
+    if (HB) {
+      Buf A, B;
+      if (i < total) issue(A, i);
+      while (i < total) {
+        if (i + NG < total) issue(B, i + NG);
+        consume(A, i);
+        i += NG;
+        if (i >= total) break;
+        if (i + NG < total) issue(A, i + NG);
+        consume(B, i);
+        i += NG;
+      }
+    } else {
+      Buf A;
+      for (; i < total; i += NG) { issue(A, i); consume(A, i); }
+    }
+    advance_to(my_tiles);                                    // release the tiles this group had no chunk in
+  }
+  tc_fence_before();
+  cluster.sync();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- L2-aware tile schedule -------------------------------------------------------------------------
+// The pair list is owner-major with u ascending inside an owner, so consecutive tiles sweep the whole
+// embedding table (295 MB of fp16 rows on the ppa shape, 2.3x the L2) once per owner and the row gathers
+// hit L2 only ~50 % of the time.  Scores are written by pair index, so the ORDER in which tiles are
+// processed is free: tiles are scheduled u-block by u-block (block = a node range whose rows fit the L2
+// budget), owners ascending inside a block — every row is then fetched from HBM about once per block
+// instead of once per owner.  tile_order[slot] = pair tile; a stable counting sort by the block of the
+// tile's first u (one CTA; a few hundred thousand tiles).  An experiment knob, see tc3_ublock_nodes.
+constexpr int TO_THREADS = 256, TO_MAX_BLOCKS = 32;     // 33 KB of static shared memory
+
+__global__ void __launch_bounds__(TO_THREADS)
+tile_order_kernel(const int *__restrict__ pu, long long M, long long ntiles, int tile_pairs, int block_nodes,
+                  int nblocks, int *__restrict__ order) {
+  __shared__ int cnt[TO_MAX_BLOCKS][TO_THREADS + 1];
+  const int t = threadIdx.x;
+  const long long per = (ntiles + TO_THREADS - 1) / TO_THREADS;
+  const long long lo = min(ntiles, (long long)t * per), hi = min(ntiles, lo + per);
+  for (int b = 0; b < nblocks; ++b) cnt[b][t] = 0;
+  for (long long i = lo; i < hi; ++i) cnt[min(__ldg(pu + i * tile_pairs) / block_nodes, nblocks - 1)][t]++;
+  __syncthreads();
+  // exclusive scan in (block, thread) order: thread b*... a single warp per block row is plenty
+  __shared__ int base[TO_MAX_BLOCKS + 1];
+  if (t < nblocks) {
+    int run = 0;
+    for (int j = 0; j < TO_THREADS; ++j) { const int c = cnt[t][j]; cnt[t][j] = run; run += c; }
+    cnt[t][TO_THREADS] = run;
+  }
+  __syncthreads();
+  if (t == 0) {
+    int run = 0;
+    for (int b = 0; b < nblocks; ++b) { base[b] = run; run += cnt[b][TO_THREADS]; }
+  }
+  __syncthreads();
+  int pos[TO_MAX_BLOCKS];
+#pragma unroll 1
+  for (int b = 0; b < nblocks; ++b) pos[b] = base[b] + cnt[b][t];
+  for (long long i = lo; i < hi; ++i) {
+    const int b = min(__ldg(pu + i * tile_pairs) / block_nodes, nblocks - 1);
+    order[pos[b]++] = (int)i;
+  }
+}
+
+// node-range size whose embedding rows fit the L2 budget; 0 = keep the natural order
+int tc3_ublock_nodes(int n, int row_bytes, long long M) {
+  // OFF by default: measured on the ppa shape (profiles/round1_e_k2_tile_schedule.md) the schedule does not
+  // pay — 64.9 ms per 4 slabs in natural order vs 65.7 / 66.7 / 66.6 / 68.3 ms with 32 / 48 / 64 / 96 MB
+  // blocks: the id warp's L2 prefetch already hides the misses, and blocking gives up the h[v] reuse of
+  // long owner runs.  EPS_TC3_UBLOCK_MB=<MB> switches it on for A/B runs.
+  int mb = 0;
+  if (const char *e = getenv("EPS_TC3_UBLOCK_MB")) mb = atoi(e);
+  if (mb <= 0) return 0;
+  const long long table = (long long)n * row_bytes, budget = (long long)mb << 20;
+  if (table <= budget || M < 8ll * n) return 0;          // table already L2-resident / too few pairs per row
+  long long nb = (table + budget - 1) / budget;
+  if (nb > TO_MAX_BLOCKS) nb = TO_MAX_BLOCKS;
+  return (int)((n + nb - 1) / nb);
+}
+
+template <int H, bool HB, int NG, int EW>
+static int tc3_launch_g(const void *h, const int *pu, const int *pv, long long M, const MlpParams &prm, int L,
+                        int apply_sigmoid, float *score, uint8_t *img, int n, int *tile_order, const TcScale *scale,
+                        cudaStream_t stream) {
+  const int nhidden = L - 1;
+  const size_t fixed = (size_t)nhidden * (H / 2) * H * 2 + (nhidden >= 2 ? (size_t)P_A2_SLOTS * TC_BM * 128 : 0) +
+                       (size_t)TC_BM * 32 + (size_t)nhidden * (H / 2) * 32 +          // bias K-step tiles
+                       sizeof(float) * (size_t)H + 2 * TC_BM * sizeof(int2) + 2 * TC_BM * sizeof(float) +
+                       sizeof(PipeBarriers);
+  const size_t budget = 227 * 1024;
+  if (fixed + (size_t)(NG + 1) * P_STAGE_BYTES > budget) return EPS_ERR_UNSUPPORTED;   // the resident weights do not fit (H = 256, L >= 4)
+  int ring = (int)std::min<size_t>((budget - fixed) / P_STAGE_BYTES, (size_t)P_MAX_RING);
+  const char *rg = getenv("EPS_TC3_RING");    // cap the ring depth (A/B measurements)
+  if (rg && atoi(rg) >= NG + 1) ring = std::min(ring, atoi(rg));
+  const size_t smem = fixed + (size_t)ring * P_STAGE_BYTES;
+  auto kern = linkpred_tc3_kernel<H, HB, NG, EW>;
+  EPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long npair_tiles = (M + 2 * TC_BM - 1) / (2 * TC_BM);
+  const int clusters = (int)std::min<long long>(npair_tiles, (long long)(sm_count() / 2));
+  const char *tn = getenv("EPS_TC3_TUNE");   // bit0: L2 row prefetch by the id warp (default on)
+  const int tune = tn ? atoi(tn) : 1;
+  const int block_nodes = tile_order ? tc3_ublock_nodes(n, H * (HB ? 2 : 4), M) : 0;
+  if (block_nodes > 0) {
+    const int nblocks = (n + block_nodes - 1) / block_nodes;
+    tile_order_kernel<<<1, TO_THREADS, 0, stream>>>(pu, M, npair_tiles, 2 * TC_BM, block_nodes, nblocks, tile_order);
+    EPS_LAUNCH_CHECK();
+  }
+  kern<<<2 * clusters, p_threads(NG, EW), smem, stream>>>(h, pu, pv, M, prm, L, apply_sigmoid, img, score, tune, ring,
+                                                     block_nodes > 0 ? tile_order : nullptr, scale);
+  EPS_LAUNCH_CHECK();
+#ifdef EPS_TC3_TRACE
+  if (const char *tf = getenv("EPS_TC3_TRACE_FILE")) {
+    cudaStreamSynchronize(stream);
+    std::vector<unsigned long long> rec(8 * TR_REGION);
+    cudaMemcpyFromSymbol(rec.data(), g_trace, rec.size() * 8);
+    if (FILE *f = fopen(tf, "wb")) { fwrite(rec.data(), 8, rec.size(), f); fclose(f); }
+    std::fill(rec.begin(), rec.end(), 0ull);
+    cudaMemcpyToSymbol(g_trace, rec.data(), rec.size() * 8);
+  }
+#endif
+  return EPS_OK;
+}
+
+template <int H, bool HB>
+static int tc3_launch_h(const void *h, const int *pu, const int *pv, long long M, const MlpParams &prm, int L,
+                        int apply_sigmoid, float *score, uint8_t *img, int n, int *tile_order, const TcScale *scale,
+                        cudaStream_t stream) {
+  // producer groups: 2 (default) or 3 (EPS_TC3_GROUPS=3); epilogue warps: 4 (default: 14 warps -> 128 registers)
+  // or 8 = two per TMEM lane quarter (EPS_TC3_EPI=8: 18 warps -> 96 registers).  Measured on the ppa-like list of
+  // tools/k2_bench.py (profiles/round2_k2_epilogue_ab.md): 7.57 ms with 4, 7.74 ms with 8 — the drain of an
+  // accumulator is paced by the TMEM read path of a lane quarter, not by the warp that issues the loads.
+  const char *g = getenv("EPS_TC3_GROUPS");
+  const char *e = getenv("EPS_TC3_EPI");
+  if (g && g[0] == '3')
+    return tc3_launch_g<H, HB, 3, 4>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, n, tile_order, scale, stream);
+  if (e && e[0] == '8')
+    return tc3_launch_g<H, HB, 2, 8>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, n, tile_order, scale, stream);
+  return tc3_launch_g<H, HB, 2, 4>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, n, tile_order, scale, stream);
+}
+
+// ---- prepare kernels: scale, fp16 table, weight images (once per (h, weights); EPS_MLP_REUSE_WORKSPACE skips them) ----
+
+// max |h| as the bit pattern of a non-negative float (orders like an unsigned integer)
+__global__ void __launch_bounds__(256) tc_absmax_kernel(const float *__restrict__ h, long long n4, unsigned int *out_bits) {
+  float m = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(h) + i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+  if (lane_id() == 0) atomicMax(out_bits, __float_as_uint(m));
+}
+
+// The power-of-two scale of the arm (tc_common.cuh).  Worst-case magnitudes, unscaled:
+//   products     P   = hmax^2
+//   layer l out  B_l = (max_n sum_k |W_l[n,k]|) * B_{l-1} + max_n |b_l[n]|,   B_0 = P
+// and S = hscale^2 = 4^a is the largest power of four with S * max(P, B_1, ..) <= 2^15 (half of fp16's largest
+// finite value), so no operand can overflow; typical magnitudes sit 10^2..10^4 below the worst case, well inside
+// fp16's normal range.  One block.
+__global__ void __launch_bounds__(256) tc_scale_kernel(const unsigned int *__restrict__ hmax_bits, const MlpParams prm,
+                                                       int H, int nhidden, TcScale *out) {
+  __shared__ double red[256];
+  const int t = threadIdx.x;
+  const float hmax = __uint_as_float(*hmax_bits);
+  double bound = (double)hmax * (double)hmax, worst = bound;
+  for (int l = 0; l < nhidden; ++l) {
+    double row = 0.0, bm = 0.0;
+    for (int n = t; n < H; n += 256) {
+      double acc = 0.0;
+      for (int k = 0; k < H; ++k) acc += fabs((double)__ldg(prm.W[l] + (size_t)n * H + k));
+      row = fmax(row, acc);
+      bm = fmax(bm, fabs((double)__ldg(prm.b[l] + n)));
+    }
+    red[t] = row;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) { if (t < o) red[t] = fmax(red[t], red[t + o]); __syncthreads(); }
+    const double rmax = red[0];
+    __syncthreads();
+    red[t] = bm;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) { if (t < o) red[t] = fmax(red[t], red[t + o]); __syncthreads(); }
+    const double bmax = red[0];
+    __syncthreads();
+    bound = rmax * bound + bmax;
+    worst = fmax(worst, bound);
+  }
+  if (t == 0) {
+    int a = 0;
+    if (worst > 0.0 && worst < 1e300) a = (int)floor(log2(32768.0 / worst) * 0.5);
+    a = max(-40, min(40, a));
+    out->hscale = exp2f((float)a);
+    out->S = exp2f((float)(2 * a));
+    out->invS = exp2f((float)(-2 * a));
+    out->hmax = hmax;
+  }
+}
+
+// fp32 embeddings -> fp16 table of h * hscale (round to nearest even), 8 elements per thread
+__global__ void __launch_bounds__(256) h_to_f16_kernel(const float *__restrict__ h, long long n8, const TcScale *__restrict__ scale,
+                                                       uint4 *__restrict__ out) {
+  const float hs = scale->hscale;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(h) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4 *>(h) + 2 * i + 1);
+    uint4 o;
+    o.x = pack_f16x2(a.x * hs, a.y * hs); o.y = pack_f16x2(a.z * hs, a.w * hs);
+    o.z = pack_f16x2(b.x * hs, b.y * hs); o.w = pack_f16x2(b.z * hs, b.w * hs);
+    out[i] = o;
+  }
+}
+
+// hidden-layer weights -> per-CTA-half fp16 SWIZZLE_128B images: [layer][half][kblock][H/2 rows][128 B]
+__global__ void pack_weights_halves_kernel(MlpParams prm, int H, int nhidden, uint8_t *img) {
+  const int chunks_per_row = H / 8, HH = H / 2;
   const int total = nhidden * H * chunks_per_row;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int l = i / (H * chunks_per_row);
@@ -34,149 +1011,17 @@ __global__ void pack_weights_kernel(MlpParams prm, int H, int nhidden, uint8_t *
     const float *w = prm.W[l] + (size_t)n * H + c * 8;
     const float4 a = *reinterpret_cast<const float4 *>(w), b = *reinterpret_cast<const float4 *>(w + 4);
     uint4 o;
-    o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
-    o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
-    *reinterpret_cast<uint4 *>(img + (size_t)l * H * H * 2 + sw128_chunk_off(H, n, c * 8)) = o;
+    o.x = pack_f16x2(a.x, a.y); o.y = pack_f16x2(a.z, a.w);
+    o.z = pack_f16x2(b.x, b.y); o.w = pack_f16x2(b.z, b.w);
+    const int half = n / HH, nn = n - half * HH;
+    *reinterpret_cast<uint4 *>(img + (size_t)l * H * H * 2 + (size_t)half * HH * H * 2 +
+                               sw128_chunk_off(HH, nn, c * 8)) = o;
   }
 }
 
-template <int H>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-linkpred_tc_kernel(const float *__restrict__ h, const int *__restrict__ pu, const int *__restrict__ pv,
-                   long long M, const MlpParams prm, int L, int apply_sigmoid,
-                   const uint8_t *__restrict__ wimg, float *__restrict__ score) {
-  static_assert(H % 64 == 0 && H >= 64 && H <= 256, "tensor-core arm: H in {64,128,192,256}");
-  constexpr int A_BYTES = TC_BM * H * 2;
-  constexpr int W_BYTES = H * H * 2;
-  constexpr uint32_t TMEM_COLS = H <= 64 ? 64 : (H <= 128 ? 128 : 256);
-  constexpr uint32_t IDESC = umma_idesc_bf16(TC_BM, H);
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t *sA = smem;
-  uint8_t *sW = smem + A_BYTES;
-  float *sBias = reinterpret_cast<float *>(smem + A_BYTES + W_BYTES);  // [(L-1)][H]
-  float *sWlast = sBias + (EPS_MAX_MLP_LAYERS - 1) * H;                // [H]
-  float *sPart = sWlast + H;                                           // [2][128]
-  __shared__ __align__(8) uint64_t mbar_mma;
-  __shared__ uint32_t tmem_base_slot;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nhidden = L - 1;
-
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 :: "r"(smem_u32(&tmem_base_slot)), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (tid == 0) {
-    mbar_init(smem_u32(&mbar_mma), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (int i = tid; i < nhidden * H; i += TC_THREADS) sBias[i] = __ldg(prm.b[i / H] + (i % H));
-  for (int i = tid; i < H; i += TC_THREADS) sWlast[i] = __ldg(prm.W[L - 1] + i);
-  const float b_last = __ldg(prm.b[L - 1]);
-  int resident_layer = -1;
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_acc = tmem_base_slot;
-  const uint32_t sA_addr = smem_u32(sA), sW_addr = smem_u32(sW), mbar_addr = smem_u32(&mbar_mma);
-  uint32_t phase = 0;
-
-  const long long ntiles = (M + TC_BM - 1) / TC_BM;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long p0 = tile * TC_BM;
-    const int rows = (int)min((long long)TC_BM, M - p0);
-    // ---- gather + Hadamard -> bf16 A tile (swizzled) ----
-    for (int r = warp; r < TC_BM; r += TC_THREADS / 32) {
-      if (r < rows) {
-        const float *hu = h + (size_t)__ldg(pu + p0 + r) * H;
-        const float *hv = h + (size_t)__ldg(pv + p0 + r) * H;
-        for (int c = lane; c < H / 8; c += 32) {
-          const float4 a0 = __ldg(reinterpret_cast<const float4 *>(hu) + 2 * c);
-          const float4 a1 = __ldg(reinterpret_cast<const float4 *>(hu) + 2 * c + 1);
-          const float4 b0 = __ldg(reinterpret_cast<const float4 *>(hv) + 2 * c);
-          const float4 b1 = __ldg(reinterpret_cast<const float4 *>(hv) + 2 * c + 1);
-          uint4 o;
-          o.x = hadamard_bf16x2(a0.x, a0.y, b0.x, b0.y); o.y = hadamard_bf16x2(a0.z, a0.w, b0.z, b0.w);
-          o.z = hadamard_bf16x2(a1.x, a1.y, b1.x, b1.y); o.w = hadamard_bf16x2(a1.z, a1.w, b1.z, b1.w);
-          *reinterpret_cast<uint4 *>(sA + sw128_chunk_off(TC_BM, r, c * 8)) = o;
-        }
-      } else {
-        for (int c = lane; c < H / 8; c += 32)
-          *reinterpret_cast<uint4 *>(sA + sw128_chunk_off(TC_BM, r, c * 8)) = make_uint4(0, 0, 0, 0);
-      }
-    }
-    float part = 0.f;
-    for (int l = 0; l < nhidden; ++l) {
-      // ---- weights of layer l -> shared memory (stay resident while only one hidden layer) ----
-      if (resident_layer != l) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(wimg + (size_t)l * W_BYTES);
-        uint4 *dst = reinterpret_cast<uint4 *>(sW);
-        for (int i = tid; i < W_BYTES / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
-        resident_layer = l;
-      }
-      fence_async_smem();   // generic-proxy smem writes (A tile, weights) -> visible to the tensor core
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-#pragma unroll
-        for (int kb = 0; kb < H / 64; ++kb) {
-#pragma unroll
-          for (int k16 = 0; k16 < 4; ++k16) {
-            const uint64_t ad = umma_smem_desc(sA_addr + kb * (TC_BM * 128) + k16 * 32);
-            const uint64_t bd = umma_smem_desc(sW_addr + kb * (H * 128) + k16 * 32);
-            umma_bf16_ss(tmem_acc, ad, bd, IDESC, (kb | k16) ? 1u : 0u);
-          }
-        }
-        umma_commit(mbar_addr);   // implies tcgen05.fence::before_thread_sync
-      }
-      mbar_wait(mbar_addr, phase);
-      phase ^= 1;
-      tc_fence_after();
-      // ---- epilogue: thread owns accumulator row (lane quadrant of its warp), half of the columns ----
-      const int row = (warp & 3) * 32 + lane;
-      const int chalf = warp >> 2;
-      const bool last_hidden = l == nhidden - 1;
-      const float *bias = sBias + l * H;
-#pragma unroll 1
-      for (int c0 = chalf * (H / 2); c0 < (chalf + 1) * (H / 2); c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem_acc + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
-        if (last_hidden) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) part = fmaf(fmaxf(v[j] + bias[c0 + j], 0.f), sWlast[c0 + j], part);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 o;
-            o.x = pack_bf16x2(fmaxf(v[j + 0] + bias[c0 + j + 0], 0.f), fmaxf(v[j + 1] + bias[c0 + j + 1], 0.f));
-            o.y = pack_bf16x2(fmaxf(v[j + 2] + bias[c0 + j + 2], 0.f), fmaxf(v[j + 3] + bias[c0 + j + 3], 0.f));
-            o.z = pack_bf16x2(fmaxf(v[j + 4] + bias[c0 + j + 4], 0.f), fmaxf(v[j + 5] + bias[c0 + j + 5], 0.f));
-            o.w = pack_bf16x2(fmaxf(v[j + 6] + bias[c0 + j + 6], 0.f), fmaxf(v[j + 7] + bias[c0 + j + 7], 0.f));
-            *reinterpret_cast<uint4 *>(sA + sw128_chunk_off(TC_BM, row, c0 + j)) = o;
-          }
-        }
-      }
-      tc_fence_before();   // TMEM reads done before the next MMA (after the barrier) overwrites
-      if (last_hidden) sPart[chalf * TC_BM + row] = part;
-    }
-    __syncthreads();
-    if (tid < TC_BM && tid < rows) {
-      float s = sPart[tid] + sPart[TC_BM + tid] + b_last;
-      score[p0 + tid] = apply_sigmoid ? sigmoidf_ref(s) : s;
-    }
-    __syncthreads();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_acc), "r"(TMEM_COLS) : "memory");
-  }
-}
-
-// The pipelined kernel gathers from a bf16 copy of h (half the bytes per pair) when the pair list
-// is long enough to amortise writing it; short lists read the caller's fp32 rows and round them in
-// registers — the SAME rounding, so the scores do not depend on this choice.
+// The kernel gathers from an fp16 copy of h (half the bytes per pair) when the pair list is long enough to
+// amortise writing it; short lists read the caller's fp32 rows and round them in registers — the SAME
+// rounding, so the scores do not depend on this choice.
 bool linkpred_tc_uses_table(int n, long long M) { return M >= 2ll * n; }
 
 static size_t tc_img_bytes(int H, int L) {
@@ -184,60 +1029,54 @@ static size_t tc_img_bytes(int H, int L) {
 }
 
 size_t linkpred_tc_workspace_bytes(int n, int H, int L, long long M) {
-  // weight images | bf16 embedding table | tile schedule of the pipelined kernel (one int per 256 pairs)
+  // header (TcScale, max |h|) | weight images | fp16 embedding table | tile schedule (one int per 256 pairs)
   return 256 + tc_img_bytes(H, L) + (linkpred_tc_uses_table(n, M) ? (((size_t)n * H * 2 + 255) & ~(size_t)255) : 0) +
          (size_t)((M + 255) / 256) * 4 + 256;
-}
-
-template <int H>
-static int tc_launch_h(const float *h, const int *pu, const int *pv, long long M, const MlpParams &prm, int L,
-                       int apply_sigmoid, float *score, uint8_t *img, cudaStream_t stream) {
-  const size_t smem = 1024 + (size_t)TC_BM * H * 2 + (size_t)H * H * 2 +
-                      sizeof(float) * ((EPS_MAX_MLP_LAYERS - 1) * H + H + 2 * TC_BM);
-  auto kern = linkpred_tc_kernel<H>;
-  EPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long ntiles = (M + TC_BM - 1) / TC_BM;
-  const int grid = (int)std::min<long long>(ntiles, (long long)sm_count());
-  kern<<<grid, TC_THREADS, smem, stream>>>(h, pu, pv, M, prm, L, apply_sigmoid, img, score);
-  EPS_LAUNCH_CHECK();
-  return EPS_OK;
 }
 
 int linkpred_tc_launch(const float *h, int n, int H, const int *pu, const int *pv, long long M,
                        const MlpParams &prm, int L, int apply_sigmoid, float *score, void *workspace,
                        size_t workspace_bytes, bool prepared, cudaStream_t stream) {
-  if (L < 2 || !(H == 64 || H == 128 || H == 256)) {
-    set_error("eps_linkpred_mlp: the tcgen05 arm needs num_layers >= 2 and H in {64,128,256} (got L=%d H=%d); "
-              "use EPS_MLP_FP32", L, H);
+  if (L < 2 || !(H == 64 || H == 128 || H == 256) || (H == 256 && L > 3)) {
+    set_error("eps_linkpred_mlp: the tcgen05 arm needs num_layers >= 2, H in {64,128,256} and its hidden-layer weights "
+              "resident in shared memory (H = 256: num_layers <= 3) (got L=%d H=%d); use EPS_MLP_FP32", L, H);
     return EPS_ERR_UNSUPPORTED;
   }
   if (!workspace || workspace_bytes < linkpred_tc_workspace_bytes(n, H, L, M)) {
     set_error("eps_linkpred_mlp: workspace too small");
     return EPS_ERR_WORKSPACE;
   }
-  uint8_t *img = (uint8_t *)workspace + 256;
-  // CTA-pair kernel (all hidden-layer weights resident) unless EPS_TC_VARIANT=1 asks for the
-  // single-CTA kernel (kept for A/B measurements)
-  const char *variant = getenv("EPS_TC_VARIANT");
-  if (!(variant && variant[0] == '1') && sm_count() >= 2) {
-    void *table = nullptr;
-    uint8_t *tail = img + ((tc_img_bytes(H, L) + 255) & ~(size_t)255);
-    if (linkpred_tc_uses_table(n, M) && !(variant && variant[0] == '2')) {
-      table = tail;
-      tail += ((size_t)n * H * 2 + 255) & ~(size_t)255;
-      if (!prepared) {                              // EPS_MLP_REUSE_WORKSPACE: the table of an earlier call is still there
-        const int st = h_to_bf16_launch(h, (long long)n * H, table, stream);
-        if (st != EPS_OK) return st;
-      }
+  uint8_t *ws = (uint8_t *)workspace;
+  TcScale *scale = (TcScale *)ws;
+  unsigned int *hmax_bits = (unsigned int *)(ws + 64);
+  uint8_t *img = ws + 256;
+  uint8_t *tail = img + tc_img_bytes(H, L);
+  const bool use_table = linkpred_tc_uses_table(n, M);
+  void *table = use_table ? tail : nullptr;
+  if (use_table) tail += ((size_t)n * H * 2 + 255) & ~(size_t)255;
+  if (!prepared) {                                  // EPS_MLP_REUSE_WORKSPACE: scale, table and images are still there
+    const int sms = sm_count();
+    EPS_CUDA(cudaMemsetAsync(hmax_bits, 0, 4, stream));
+    const long long n4 = (long long)n * H / 4;
+    tc_absmax_kernel<<<(int)std::min<long long>((n4 + 255) / 256, (long long)sms * 16), 256, 0, stream>>>(h, n4, hmax_bits);
+    tc_scale_kernel<<<1, 256, 0, stream>>>(hmax_bits, prm, H, L - 1, scale);
+    if (use_table) {
+      const long long n8 = (long long)n * H / 8;
+      h_to_f16_kernel<<<(int)std::min<long long>((n8 + 255) / 256, (long long)sms * 16), 256, 0, stream>>>(
+          h, n8, scale, reinterpret_cast<uint4 *>(table));
     }
-    return linkpred_tc2_launch(h, table, H, pu, pv, M, prm, L, apply_sigmoid, score, img, n, (int *)tail, prepared, stream);
+    const int total = (L - 1) * H * (H / 8);
+    pack_weights_halves_kernel<<<(total + 255) / 256, 256, 0, stream>>>(prm, H, L - 1, img);
+    EPS_LAUNCH_CHECK();
   }
-  const int total = (L - 1) * H * (H / 8);
-  pack_weights_kernel<<<(total + 255) / 256, 256, 0, stream>>>(prm, H, L - 1, img);
-  EPS_LAUNCH_CHECK();
-  if (H == 64) return tc_launch_h<64>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, stream);
-  if (H == 128) return tc_launch_h<128>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, stream);
-  return tc_launch_h<256>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, stream);
+  int *tile_order = (int *)tail;
+#define EPS_TC3(HV)                                                                                                              \
+  return use_table ? tc3_launch_h<HV, true>(table, pu, pv, M, prm, L, apply_sigmoid, score, img, n, tile_order, scale, stream)  \
+                   : tc3_launch_h<HV, false>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, n, tile_order, scale, stream)
+  if (H == 64) { EPS_TC3(64); }
+  if (H == 128) { EPS_TC3(128); }
+  EPS_TC3(256);
+#undef EPS_TC3
 }
 
 }  // namespace eps

@@ -166,7 +166,7 @@ class LinkPredictor(nn.Module):
         self.lins = nn.ModuleList(nn.Linear(dims[i], dims[i + 1]) for i in range(num_layers))
         self.dropout = dropout
         # K2 arm: "prefilter" (default) = fp32 results everywhere; the filter step additionally uses the tcgen05
-        # arm to preselect the band around its top-k (filter_step.FilterJob); "fp32" / "bf16" force one arm
+        # arm to preselect the band around its top-k (filter_step.FilterJob); "fp32" / "f16" force one arm
         self.precision = "prefilter"
 
     def reset_parameters(self):
@@ -175,15 +175,15 @@ class LinkPredictor(nn.Module):
 
     def score_pairs(self, h: torch.Tensor, edges: torch.Tensor, precision: Optional[str] = None) -> torch.Tensor:
         """sigmoid(MLP(h[u]*h[v])) for edges [2,B] -> [B]; gather fused into the kernel.  ``precision``:
-        "fp32" (FFMA, reference arithmetic) or "bf16" (tcgen05); default ``self.precision`` ("prefilter", the
+        "fp32" (FFMA, reference arithmetic) or "f16" (tcgen05, fp16 operands; alias "bf16"); default ``self.precision`` ("prefilter", the
         filter step's two-stage mode, scores a plain pair list in fp32)."""
         prec = precision or self.precision
         return ops.linkpred_mlp(h, edges, [l.weight for l in self.lins], [l.bias for l in self.lins],
                                 precision="fp32" if prec == "prefilter" else prec, sigmoid=True)
 
     def tc_context(self, h: torch.Tensor) -> "ops.LinkpredTC":
-        """The tcgen05 arm bound to ``h`` and the current weights for a series of slabs (bf16 table and weight
-        images built once): ``ctx.score(edges)`` == ``score_pairs(h, edges, "bf16")``."""
+        """The tcgen05 arm bound to ``h`` and the current weights for a series of slabs (fp16 table and weight
+        images built once): ``ctx.score(edges)`` == ``score_pairs(h, edges, "f16")``."""
         return ops.LinkpredTC(h, [l.weight for l in self.lins], [l.bias for l in self.lins])
 
     def forward(self, x_i, x_j):

@@ -10,7 +10,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import (EPS_CN_GROUPED_BY_V, EPS_CN_SIGMOID, EPS_MLP_FP32, EPS_MLP_REUSE_WORKSPACE, EPS_MLP_TC_BF16,
+from ._lib import (EPS_CN_GROUPED_BY_V, EPS_CN_SIGMOID, EPS_MLP_FP32, EPS_MLP_REUSE_WORKSPACE, EPS_MLP_TC_F16,
                    EPS_REDUCE_MEAN, EPS_REDUCE_SUM, EpsError, check)
 from .graph import SparseAdj
 
@@ -104,6 +104,11 @@ def cn_aa(adj: SparseAdj, edges: torch.Tensor, wtable: Optional[torch.Tensor] = 
     return (score, count) if want_count else score
 
 
+# K2 arms: "fp32" = FFMA (reference arithmetic); "f16" = tcgen05 tensor cores, fp16 operands / fp32 accumulate
+# ("tc" and the round-1 name "bf16" are aliases)
+MLP_PRECISIONS = {"fp32": EPS_MLP_FP32, "f16": EPS_MLP_TC_F16, "tc": EPS_MLP_TC_F16, "bf16": EPS_MLP_TC_F16}
+
+
 def linkpred_mlp(h: torch.Tensor, edges: torch.Tensor, weights: Sequence[torch.Tensor],
                  biases: Sequence[torch.Tensor], precision: str = "fp32", sigmoid: bool = True) -> torch.Tensor:
     """K2.  sigmoid(MLP(h[u] * h[v])) for every pair."""
@@ -120,23 +125,41 @@ def linkpred_mlp(h: torch.Tensor, edges: torch.Tensor, weights: Sequence[torch.T
         want = (1 if l == L - 1 else H, H)
         if tuple(w.shape) != want:
             raise EpsError(f"linkpred layer {l}: weight shape {tuple(w.shape)} != {want}")
-    prec = {"fp32": EPS_MLP_FP32, "bf16": EPS_MLP_TC_BF16, "tc": EPS_MLP_TC_BF16}[precision]
+    prec = MLP_PRECISIONS[precision]
     Wp = (C.c_void_p * L)(*[w.data_ptr() for w in Ws])
     bp = (C.c_void_p * L)(*[b.data_ptr() for b in bs])
     score = torch.empty(M, dtype=torch.float32, device=h.device)
     ws = _ws(lib.eps_linkpred_workspace_bytes(n, H, L, M, prec), h.device)
     check(lib.eps_linkpred_mlp(_ptr(h), n, H, _ptr(pu), _ptr(pv), M, Wp, bp, L, prec, int(sigmoid),
                                _ptr(score), _ptr(ws), ws.numel(), _stream()), "eps_linkpred_mlp")
-    LAUNCHES["n"] += ((3 if M >= 2 * n else 2) if prec == EPS_MLP_TC_BF16 else 1) if M else 0
+    LAUNCHES["n"] += ((5 if M >= 2 * n else 4) if prec == EPS_MLP_TC_F16 else 1) if M else 0
     return score
+
+
+def tc_scale(h: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor]):
+    """Host restatement of the tensor-core arm's power-of-two scale (csrc/linkpred_tc.cu tc_scale_kernel), for
+    tests and diagnostics: ``(hscale, S)`` with S = hscale^2 = 4^a, a = floor(log2(2^15 / worst) / 2), where
+    ``worst`` is the largest worst-case magnitude among the Hadamard products (max|h|^2) and the hidden layers'
+    outputs (B_l = max row L1 norm of W_l * B_{l-1} + max|b_l|)."""
+    import math
+    bound = float(h.abs().max().item()) ** 2
+    worst = bound
+    for w, b in zip(weights[:-1], biases[:-1]):
+        bound = float(w.double().abs().sum(1).max().item()) * bound + float(b.abs().max().item())
+        worst = max(worst, bound)
+    a = 0
+    if 0.0 < worst < 1e300:
+        a = int(math.floor(math.log2(32768.0 / worst) * 0.5))
+    a = max(-40, min(40, a))
+    return 2.0 ** a, 4.0 ** a
 
 
 class LinkpredTC:
     """K2's tcgen05 arm bound to ONE embedding matrix and ONE set of weights for a series of calls (the ~100
-    owner slabs of a filter job): the bf16 copy of ``h`` and the packed weight images live in a workspace this
+    owner slabs of a filter job): the scale, the fp16 copy of ``h`` and the packed weight images live in a workspace this
     object owns and are built by the first long call only (EPS_MLP_REUSE_WORKSPACE afterwards).  ``h`` and the
     weights are held by reference and must not be modified while the object is in use.  Same scores, bit for
-    bit, as ``linkpred_mlp(..., precision="bf16")``."""
+    bit, as ``linkpred_mlp(..., precision="f16")``."""
 
     def __init__(self, h: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor]):
         _need_cuda(h, *weights, *biases)
@@ -152,19 +175,19 @@ class LinkpredTC:
         L = len(self.Ws)
         pu, pv = _pairs(edges)
         M = pu.numel()
-        if M < 2 * n:                      # short list: no bf16 table in the workspace, nothing to reuse
-            return linkpred_mlp(self.h, edges, self.Ws, self.bs, "bf16", sigmoid)
-        need = int(lib.eps_linkpred_workspace_bytes(n, H, L, M, EPS_MLP_TC_BF16))
+        if M < 2 * n:                      # short list: no fp16 table in the workspace, nothing to reuse
+            return linkpred_mlp(self.h, edges, self.Ws, self.bs, "f16", sigmoid)
+        need = int(lib.eps_linkpred_workspace_bytes(n, H, L, M, EPS_MLP_TC_F16))
         if self.ws is None or self.ws.numel() < need:
             self.ws = _ws(need + (M // 256) * 2, self.h.device)      # headroom for somewhat longer slabs
             self.prepared = False
         Wp = (C.c_void_p * L)(*[w.data_ptr() for w in self.Ws])
         bp = (C.c_void_p * L)(*[b.data_ptr() for b in self.bs])
         score = torch.empty(M, dtype=torch.float32, device=self.h.device)
-        prec = EPS_MLP_TC_BF16 | (EPS_MLP_REUSE_WORKSPACE if self.prepared else 0)
+        prec = EPS_MLP_TC_F16 | (EPS_MLP_REUSE_WORKSPACE if self.prepared else 0)
         check(lib.eps_linkpred_mlp(_ptr(self.h), n, H, _ptr(pu), _ptr(pv), M, Wp, bp, L, prec, int(sigmoid),
                                    _ptr(score), _ptr(self.ws), self.ws.numel(), _stream()), "eps_linkpred_mlp")
-        LAUNCHES["n"] += 1 if self.prepared else 3
+        LAUNCHES["n"] += 1 if self.prepared else 5
         self.prepared = True
         return score
 

@@ -14,7 +14,7 @@ Differences from the reference, all on the fast side of the same semantics:
     "score desc, then (v, u) asc" (the reference's unstable CPU sort leaves ties arbitrary);
   * ``--topk K`` keeps only the first K rows (rank.py only ever reads a prefix, rank.py:294);
     without it every candidate is written, like the reference;
-  * with ``--topk`` a GNN filter scores every candidate on the tcgen05 tensor cores (bf16 operands) and
+  * with ``--topk`` a GNN filter scores every candidate on the tcgen05 tensor cores (fp16 operands) and
     re-scores the band around the k-th score in fp32: the saved list is the fp32 list, bit for bit
     (``--mlp_precision``, filter_step.filter_topk_multi);
   * under ``torchrun`` the owners are sharded across the GPUs and merged with one all-gather.
@@ -45,10 +45,10 @@ def parse_args(argv=None):
     p.add_argument("--device", type=int, default=0)
     # additions
     p.add_argument("--topk", type=int, default=None, help="keep only the K best rows (default: all)")
-    p.add_argument("--mlp_precision", choices=["prefilter", "fp32", "bf16"], default="prefilter",
-                   help="GNN filters: 'prefilter' = tcgen05 bf16 scores select a band around the top-k that is "
+    p.add_argument("--mlp_precision", choices=["prefilter", "fp32", "f16", "bf16"], default="prefilter",
+                   help="GNN filters: 'prefilter' = tcgen05 fp16-operand scores select a band around the top-k that is "
                         "re-scored in fp32 (the fp32 list, bit for bit); 'fp32' = FFMA arm for every candidate; "
-                        "'bf16' = tensor-core scores only (approximate list)")
+                        "'f16' (alias 'bf16') = tensor-core scores only (approximate list)")
     p.add_argument("--slab_pairs", type=int, default=1 << 27)
     p.add_argument("--random_init", action="store_true",
                    help="score with seeded random weights when models/{checkpoint} does not exist")

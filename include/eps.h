@@ -119,12 +119,18 @@ size_t eps_cn_aa_workspace_bytes(void);
  * W_h / b_h: HOST arrays of L device pointers; W_l is [out,in] row-major fp32
  * (nn.Linear layout): [H,H] for l < L-1 and [1,H] for the last layer.
  * precision: EPS_MLP_FP32    fp32 FFMA on CUDA cores (reference arithmetic)
- *            EPS_MLP_TC_BF16 bf16 operands, fp32 accumulate, tcgen05.mma + TMEM
+ *            EPS_MLP_TC_F16  tcgen05.mma + TMEM: IEEE fp16 operands under a power-of-two scale derived on the
+ *                            device from worst-case bounds (no overflow possible; the scale drops out exactly
+ *                            at the output layer), fp32 accumulation / output layer / sigmoid.  Needs
+ *                            num_layers >= 2, H in {64, 128, 256} and H = 256 -> num_layers <= 3 (the hidden
+ *                            layers' weights stay resident in shared memory); EPS_ERR_UNSUPPORTED otherwise
+ *                            (e.g. H = 300 of the email config: use EPS_MLP_FP32).
  * ------------------------------------------------------------------------- */
 #define EPS_MLP_FP32 0
-#define EPS_MLP_TC_BF16 1
-/* OR-ed into `precision` with EPS_MLP_TC_BF16: `workspace` is the buffer of an EARLIER call with the same h
- * (contents), weights, n, H and L, and both calls have M >= 2n (the bf16 copy of h exists) — the bf16 table
+#define EPS_MLP_TC_F16 1
+#define EPS_MLP_TC_BF16 EPS_MLP_TC_F16 /* round-1 name of the tensor-core arm (its operands were bf16 then) */
+/* OR-ed into `precision` with EPS_MLP_TC_F16: `workspace` is the buffer of an EARLIER call with the same h
+ * (contents), weights, n, H and L, and both calls have M >= 2n (the fp16 copy of h exists) — the scale, the fp16 table
  * and the weight images in it are reused instead of rebuilt (one filter job scores ~100 slabs against the
  * same embeddings).  The workspace must be at least eps_linkpred_workspace_bytes(n, H, L, M_max, ...) for
  * the largest M of the series; its layout does not depend on M except for the tail. */

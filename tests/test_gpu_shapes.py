@@ -21,7 +21,7 @@ import scipy.sparse as ssp
 import torch
 
 from oracle import gnn as ognn, graph as og, heuristics as oh, ranking as orank
-from util import synth_graph, to_adj
+from util import spread_linkpred, synth_graph, to_adj
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -88,6 +88,8 @@ def test_ddi_shape_full_filter_cn_bit_exact_and_prefilter_identical():
     assert e2.shape[1] == cand.shape[1] and np.array_equal(aa2.cpu().numpy()[pick], aa)
     # GCN filter (the ddi recipe): prefilter list == fp32-arm list, bit for bit
     mg, sd = _gcn_model(g.n, 256, 2, 0)
+    spread_linkpred(mg, None, adj, e)                             # trained-like score spread (see util)
+    sd = {k_: v.detach().cpu() for k_, v in mg.state_dict().items()}
     st16, st32 = {}, {}
     l32 = filter_step.filter_topk("gcn", mg, None, adj, k=k, slab_pairs=1 << 23, precision="fp32", stats=st32)
     l16 = filter_step.filter_topk("gcn", mg, None, adj, k=k, slab_pairs=1 << 23, precision="prefilter", stats=st16)
@@ -95,13 +97,14 @@ def test_ddi_shape_full_filter_cn_bit_exact_and_prefilter_identical():
     info = st16["prefilter"]["gcn"]
     print("ddi prefilter:", info)
     assert torch.equal(l16, l32)
-    assert info["max_abs_dev_bf16_vs_fp32"] <= filter_step.PREFILTER_TOL
+    assert info["max_abs_dev_tc_vs_fp32"] <= info["tol"] <= filter_step.PREFILTER_TOL
+    assert info["pool"] < cand.shape[1] // 2                      # the band did prune
     # and the fp32 list itself is the oracle's (scores within 1e-5 of fp64, order consistent with them)
     top = l32.cpu().numpy()
     h64 = ognn.gcn_forward(g, sd["emb.weight"], sd, 2, torch.float64)
     uv = top[:20000, :2].astype(np.int64).T
     sc64 = ognn.linkpred_forward(h64, uv, sd, 2, torch.float64).numpy()
-    assert np.max(np.abs(top[:20000, 2] - sc64)) <= 1e-5
+    assert np.max(np.abs(top[:20000, 2] - sc64)) <= 5e-5          # fp32 vs fp64 on the rescaled (ill-conditioned) output layer
 
 
 @pytest.mark.timeout(600)
@@ -165,11 +168,14 @@ def test_ppa_shape_slab_vs_oracle_and_prefilter_identical():
     # GCN + LinkPredictor on the slab: prefilter == fp32 arm, bit for bit
     x = torch.from_numpy(s["x"]).to(DEV)
     mg, sd = _gcn_model(g.n, 256, 3, s["x"].shape[1])
-    k = 1_000_000
+    spread_linkpred(mg, x, adj, torch.from_numpy(e_np).to(DEV))    # trained-like score spread (see util)
+    k = 250_000
     st16 = {}
     l32 = filter_step.filter_topk("gcn", mg, x, adj, k=k, slab_pairs=1 << 25, precision="fp32", owners=(0, v_hi))
     l16 = filter_step.filter_topk("gcn", mg, x, adj, k=k, slab_pairs=1 << 25, precision="prefilter", owners=(0, v_hi),
                                   stats=st16)
     assert "prefilter_fallback" not in st16
-    print("ppa slab prefilter:", st16["prefilter"]["gcn"], "survivors", st16["pushdown_survivors"])
+    info = st16["prefilter"]["gcn"]
+    print("ppa slab prefilter:", info, "survivors", st16["pushdown_survivors"])
     assert torch.equal(l16, l32)
+    assert info["pool"] < 40 * k                                  # the band did prune (the slab holds > 160 k)

@@ -90,13 +90,13 @@ def test_gpu_linkpred_fp32_matches_reference_vectors(H, L):
 @pytest.mark.gpu
 @pytest.mark.parametrize("H,L", [(64, 2), (256, 3)])
 def test_gpu_linkpred_tcgen05_matches_reference_vectors(H, L):
-    """K2 tcgen05 arm (bf16 operands, fp32 accumulate): |sigma - reference| <= 2e-3."""
+    """K2 tcgen05 arm (fp16 operands, fp32 accumulate): |sigma - reference| <= 3e-4."""
     from edge_proposal_sets_b200.models import LinkPredictor
     x_i, x_j, y, sd = _case(H, L)
     dev = torch.device("cuda:0")
     lp = LinkPredictor(H, H, 1, L, 0.5).to(dev)
     lp.load_state_dict({k.replace("linkpred.", ""): v for k, v in sd.items()})
     lp.eval()
-    lp.precision = "bf16"
+    lp.precision = "f16"
     got = lp(x_i.to(dev), x_j.to(dev)).cpu().numpy()
-    np.testing.assert_allclose(got, y, rtol=0, atol=2e-3)
+    np.testing.assert_allclose(got, y, rtol=0, atol=3e-4)

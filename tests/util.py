@@ -64,3 +64,25 @@ def csr_from_undirected(n, und_edges, dataset="x", weight=None):
     ei = np.concatenate([e.T, e[:, ::-1].T], axis=1)
     w = np.ones(ei.shape[1], np.float32) if weight is None else np.concatenate([weight, weight]).astype(np.float32)
     return og.add_edges(dataset, ei, w, np.zeros((2, 0), np.int64), n)
+
+
+def spread_linkpred(model, x, adj, sample_edges):
+    """Give a seeded random LinkGNN the score spread of a TRAINED filter model (what bench.py does to its synthetic
+    model): zero hidden biases and He-uniform hidden weights in the LinkPredictor, output layer rescaled so that the
+    fp32 logits of ``sample_edges`` have mean -2 and std 2.  With nn.Linear's default init every candidate scores
+    the same to ~1e-4 and a top-k boundary means nothing."""
+    from edge_proposal_sets_b200 import ops
+    lins = model.linkpred.lins
+    with torch.no_grad():
+        for lin in lins[:-1]:
+            lin.weight.mul_(6.0 ** 0.5)
+            lin.bias.zero_()
+        lins[-1].bias.zero_()
+        h = model.embed(x, adj)
+        logit = ops.linkpred_mlp(h, sample_edges, [l.weight for l in lins], [l.bias for l in lins], "fp32", sigmoid=False)
+        mean, std = float(logit.double().mean()), float(logit.double().std())
+        scale = 2.0 / max(std, 1e-30)
+        lins[-1].weight.mul_(scale)
+        lins[-1].bias.fill_(-mean * scale - 2.0)
+    model._h_key = None
+    return model

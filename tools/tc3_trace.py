@@ -25,10 +25,10 @@ def run():
     Ws = [torch.randn(H, H, generator=g).cuda() / 16 for _ in range(L - 1)] + [torch.randn(1, H, generator=g).cuda() / 16]
     bs = [torch.randn(H, generator=g).cuda() / 16 for _ in range(L - 1)] + [torch.zeros(1).cuda()]
     for _ in range(2):
-        ops.linkpred_mlp(h, e, Ws, bs, "bf16")
+        ops.linkpred_mlp(h, e, Ws, bs, "f16")
     torch.cuda.synchronize()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record(); ops.linkpred_mlp(h, e, Ws, bs, "bf16"); t1.record(); torch.cuda.synchronize()
+    t0.record(); ops.linkpred_mlp(h, e, Ws, bs, "f16"); t1.record(); torch.cuda.synchronize()
     print("M", M, "ms", t0.elapsed_time(t1))
 
 
