@@ -93,8 +93,10 @@ def block_matmul(x: torch.Tensor, w: torch.Tensor, lo: int, hi: int, n: int,
 
 def allgather_row_slabs(local: torch.Tensor, bounds: List[int], group=None) -> torch.Tensor:
     """rows [bounds[r], bounds[r+1]) from every rank r -> the full [n, F] matrix on every rank.
-    One ``all_gather_into_tensor`` of slabs padded to the largest range (NCCL wants equal sizes)."""
-    rank, world = world_info()
+    One ``all_gather_into_tensor`` of slabs padded to the largest range (NCCL wants equal sizes).  The number
+    of ranks is what ``bounds`` says (a non-distributed call inside an initialised process group has
+    ``bounds == [0, n]`` and gathers nothing)."""
+    world = len(bounds) - 1
     n, F = bounds[-1], local.shape[1]
     if world == 1:
         return local
