@@ -669,10 +669,9 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
     // 8 K-elements = one 16-byte unit of the swizzled stage; a warp instruction covers 8 rows, and
     // rows that share v (the common case inside a run of the column-major candidate order) coalesce
     // into one request.
-    //   HB (fp16 copy of h, the hot path): 2 x LDG.128 per row (u, v) -> 8 loads per chunk, and the
-    //       loads of the NEXT chunk are issued before the current one is converted (two register
-    //       buffers), so every producer thread keeps 8-16 x 16 B in flight (~75 KB per SM);
-    //   fp32 source (small pair lists, no table): 4 x LDG.128 per row, one chunk in flight.
+    //   HB (fp16 copy of h, the hot path): cp.async of the h[u] pieces straight into the ring stage, multiplied
+    //       in place by h[v] when they have landed (see issue_async / process below);
+    //   fp32 source (small pair lists, no table): 4 x LDG.128 per row into registers, one chunk in flight.
     const int pw = warp - P_FIRST_PROD_WARP;                 // 0..11
     const int group = pw / P_GROUP_WARPS;
     const int t = (pw % P_GROUP_WARPS) * 32 + lane;          // 0..127
@@ -723,6 +722,18 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
       const int boff = (c * P_CHUNK_K + l4 * 8) * (HB ? 2 : 4);
       if (t == 0) TR(8, c, group);
       b.valid = 0;
+      if (tune & 4) {            // EXPERIMENT (EPS_TC3_TUNE bit 2): no gathers at all — the kernel's time without them
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          b.v[q] = idv[q];
+          if (idu[q] >= 0) b.valid |= 1u << q;
+#pragma unroll
+          for (int j = 0; j < LPR; ++j) b.xu[q][j] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+        }
+#pragma unroll
+        for (int j = 0; j < LPR; ++j) b.xv[j] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+        return;
+      }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         b.v[q] = idv[q];
@@ -758,10 +769,19 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
           uint4 xv[LPR];
 #pragma unroll
           for (int j = 0; j < LPR; ++j) xv[j] = b.xv[j];
-          if (q > 0 && b.v[q] != b.v[0]) {
+          if (q > 0) {
+            // A row whose v differs from the buffer's (a run boundary, or an arbitrary pair list) fetches its own
+            // copy — as a PREDICATED load.  Written as `if (v[q] != v[0]) xv = __ldg(..)` the compiler turned it
+            // into an UNCONDITIONAL load from a selected address (round-2 SASS: three dependent LDG.E.128 per
+            // chunk in front of the HMUL2s), i.e. every chunk waited for three serial L1/L2 round trips and the
+            // first layer ran at half the tensor pipe's pace (profiles/round2_b_tc_timeline.md).
             const uint4 *pv4 = reinterpret_cast<const uint4 *>(hbase + (size_t)b.v[q] * ROW_BYTES + boff);
 #pragma unroll
-            for (int j = 0; j < LPR; ++j) xv[j] = __ldg(pv4 + j);
+            for (int j = 0; j < LPR; ++j)
+              asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, %6;\n\t"
+                           "@p ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}\n"
+                           : "+r"(xv[j].x), "+r"(xv[j].y), "+r"(xv[j].z), "+r"(xv[j].w)
+                           : "l"(pv4 + j), "r"(b.v[q]), "r"(b.v[0]));
           }
           if (HB) {
             o.x = mul_f16x2(b.xu[q][0].x, xv[0].x); o.y = mul_f16x2(b.xu[q][0].y, xv[0].y);
@@ -782,8 +802,76 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
       if (t == 0) TR(10, (int)(i % NCHUNK), group);
     };
 
+    // ---- fp16-table path: the gathered rows land IN the ring stage (cp.async, 16 B per row and thread, already at
+    // their swizzled position) and are multiplied by h[v] in place once they have arrived.  cp.async groups are
+    // waited for by AGE (wait_group 1 = everything but the newest), so the rows of the next chunk stay in flight
+    // while the current chunk is multiplied — with register buffers the first use of a buffer also waited for the
+    // loads issued after it (one scoreboard), and the first layer ran at ~550 clocks per chunk for 256 clocks of
+    // MMA work (profiles/round2_b_tc_timeline.md).  Nothing but the 16-byte h[v] piece lives in registers.
+    struct St { int v[4]; uint32_t valid, stage; int boff; uint4 xv; };
+    auto issue_async = [&](St &st, long long i) {
+      const long long tl = i / NCHUNK;
+      const int c = (int)(i - tl * NCHUNK);
+      if (tl != cur_tl) {
+        advance_to(tl);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int2 id = sIds[(tl & 1) * TC_BM + rg + 32 * q];
+          idu[q] = id.x; idv[q] = id.y;
+        }
+      }
+      const uint32_t stage = pstage;
+      mbar_wait_cluster(smem_u32(&bars.empty[stage]), pphase);   // the MMAs that read this stage retired
+      pstage += NG;
+      if (pstage >= (uint32_t)ring) { pstage -= (uint32_t)ring; pphase ^= 1u; }
+      if (t == 0) TR(8, c, group);
+      st.stage = stage;
+      st.boff = (c * P_CHUNK_K + l4 * 8) * 2;
+      st.valid = 0;
+      const uint32_t dst0 = smem_u32(sRing + stage * P_STAGE_BYTES);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        st.v[q] = idv[q];
+        const bool ok = idu[q] >= 0;
+        if (ok) st.valid |= 1u << q;
+        const char *src = hbase + (ok ? (size_t)idu[q] * ROW_BYTES + st.boff : (size_t)0);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                     :: "r"(dst0 + sw64_chunk_off(rg + 32 * q, l4)), "l"(src), "r"(ok ? 16 : 0) : "memory");   // 0: zero fill
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      st.xv = make_uint4(0u, 0u, 0u, 0u);
+      if (st.valid) st.xv = __ldg(reinterpret_cast<const uint4 *>(hbase + (size_t)idv[0] * ROW_BYTES + st.boff));
+    };
+    auto process = [&](St &st, bool newer_in_flight) {
+      if (newer_in_flight) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (t == 0) TR(9, (int)(st.boff >> 6), group);
+      uint8_t *dst = sRing + st.stage * P_STAGE_BYTES;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 *cell = reinterpret_cast<uint4 *>(dst + sw64_chunk_off(rg + 32 * q, l4));
+        const uint4 xu = *cell;
+        uint4 xv = st.xv;
+        if (q > 0) {          // a row of another owner (run boundary, arbitrary pair list) fetches its own h[v] piece
+          const uint4 *pv4 = reinterpret_cast<const uint4 *>(hbase + (size_t)st.v[q] * ROW_BYTES + st.boff);
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, %6;\n\t"
+                       "@p ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}\n"
+                       : "+r"(xv.x), "+r"(xv.y), "+r"(xv.z), "+r"(xv.w) : "l"(pv4), "r"(st.v[q]), "r"(st.v[0]));
+        }
+        uint4 o;
+        o.x = mul_f16x2(xu.x, xv.x); o.y = mul_f16x2(xu.y, xv.y);
+        o.z = mul_f16x2(xu.z, xv.z); o.w = mul_f16x2(xu.w, xv.w);
+        if (!((st.valid >> q) & 1u)) o = make_uint4(0u, 0u, 0u, 0u);
+        *cell = o;
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.full[st.stage]), 0);
+      if (t == 0) TR(10, (int)(st.boff >> 6), group);
+    };
+
     long long i = group;
-    if (HB) {
+    if (HB && (tune & 8)) {               // EPS_TC3_TUNE bit 3: register double buffer (A/B against cp.async below)
       Buf A, B;
       if (i < total) issue(A, i);
       while (i < total) {
@@ -793,6 +881,20 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
         if (i >= total) break;
         if (i + NG < total) issue(A, i + NG);
         consume(B, i);
+        i += NG;
+      }
+    } else if (HB) {
+      St A, B;
+      if (i < total) issue_async(A, i);
+      while (i < total) {
+        bool nxt = i + NG < total;
+        if (nxt) issue_async(B, i + NG);
+        process(A, nxt);
+        i += NG;
+        if (i >= total) break;
+        nxt = i + NG < total;
+        if (nxt) issue_async(A, i + NG);
+        process(B, nxt);
         i += NG;
       }
     } else {
@@ -886,7 +988,7 @@ static int tc3_launch_g(const void *h, const int *pu, const int *pv, long long M
   const long long npair_tiles = (M + 2 * TC_BM - 1) / (2 * TC_BM);
   const int clusters = (int)std::min<long long>(npair_tiles, (long long)(sm_count() / 2));
   const char *tn = getenv("EPS_TC3_TUNE");   // bit0: L2 row prefetch by the id warp (default on)
-  const int tune = tn ? atoi(tn) : 1;
+  const int tune = tn ? atoi(tn) : 9;   // bit3: register double buffer (measured faster than cp.async into a 4-stage ring: 8.56 vs 10.02 ms, gpurun_out/r2i_k2.log)
   const int block_nodes = tile_order ? tc3_ublock_nodes(n, H * (HB ? 2 : 4), M) : 0;
   if (block_nodes > 0) {
     const int nblocks = (n + block_nodes - 1) / block_nodes;
