@@ -25,6 +25,7 @@
 #include <cooperative_groups.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <vector>
@@ -35,8 +36,8 @@ namespace eps {
 
 namespace cg = cooperative_groups;
 
-constexpr int P_MAX_RING = 8;                                      // first-layer ring stages (8 KB each), chosen at launch
-constexpr int P_A2_SLOTS = 3;                                      // activation K-block ring (16 KB each)
+constexpr int P_MAX_RING = 10;                                     // first-layer ring stages (8 KB each), chosen at launch
+constexpr int P_MAX_CHUNKS = 8;                                    // 32-column K-chunks per layer at H = 256
 constexpr int P_GROUP_WARPS = 4;                                   // warps per producer group
 // Warp roles: EW epilogue warps (4, or 8 = two per TMEM lane quarter, see the epilogue), then the MMA warp,
 // the pair-id warp and NG producer groups of four warps each.
@@ -118,6 +119,22 @@ __device__ __forceinline__ void umma_f16_ss_2cta_p(uint32_t tmem_d, uint64_t ade
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}\n"
       :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
+// A operand from TENSOR MEMORY (lane = row, one 32-bit column = two consecutive K elements), B from shared memory
+__device__ __forceinline__ void umma_f16_ts_2cta_p(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc,
+                                                    uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}\n"
+      :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+      :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit_mc(uint32_t mbar_saddr) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -173,8 +190,7 @@ struct PipeBarriers {
   uint64_t empty[P_MAX_RING];  // MMA commit -> producers                    (multicast, both CTAs)
   uint64_t acc_full[2];        // MMA commit -> epilogue                     (multicast, both CTAs)
   uint64_t acc_free[2];        // epilogue (both CTAs) -> MMA issuer         (waited in the leader)
-  uint64_t a2_full[P_A2_SLOTS];   // epilogue (both CTAs) -> MMA issuer: a 64-column K-block of activations is in place
-  uint64_t a2_empty[P_A2_SLOTS];  // MMA commit -> epilogue                 (multicast, both CTAs)
+  uint64_t a2_full[P_MAX_CHUNKS];  // epilogue (both CTAs) -> MMA issuer: 32-column chunk c of the activations is in TMEM
   uint64_t ids_full[2];        // ids warp -> producers                      (CTA-local)
   uint64_t ids_empty[2];       // producers -> ids warp                      (CTA-local)
   uint32_t tmem_base_slot;
@@ -184,15 +200,6 @@ __device__ __forceinline__ uint32_t cvt_relu_f16x2(float lo, float hi) {
   uint32_t d;
   asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));   // max(x, 0) then RN to fp16
   return d;
-}
-__device__ __forceinline__ float2 add_f32x2(float2 a, float2 b) {   // FADD2: two fp32 adds, one issue slot
-  unsigned long long pa, pb, pr;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(pa) : "f"(a.x), "f"(a.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(pb) : "f"(b.x), "f"(b.y));
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(pr) : "l"(pa), "l"(pb));
-  float2 r;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(pr));
-  return r;
 }
 __device__ __forceinline__ float2 fma_f32x2(float2 a, float2 b, float2 c) {
   unsigned long long pa, pb, pc, pr;
@@ -204,7 +211,6 @@ __device__ __forceinline__ float2 fma_f32x2(float2 a, float2 b, float2 c) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(pr));
   return r;
 }
-
 template <int H, bool HB /* h is the fp16 table (else fp32) */, int NG /* producer groups */, int EW /* epilogue warps */>
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(p_maxreg(NG, EW))
 linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, const int *__restrict__ pv,
@@ -212,11 +218,10 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
                     const uint8_t *__restrict__ wimg, float *__restrict__ score, int tune, int ring,
                     const int *__restrict__ tile_order, const TcScale *__restrict__ scale) {
   static_assert(H % 64 == 0 && H >= 64 && H <= 256, "H in {64,128,192,256}");
+  static_assert(EW == 4, "one epilogue warp per TMEM lane quarter (the in-place conversion relies on program order per lane)");
   constexpr int HH = H / 2;
   constexpr int WH_BYTES = HH * H * 2;
-  constexpr int A2_SLOT_BYTES = TC_BM * 128;                  // 128 rows x 64 K fp16, SWIZZLE_128B
-  constexpr int NCHUNK = H / P_CHUNK_K;
-  constexpr int NKB = H / 64;
+  constexpr int NCHUNK = H / P_CHUNK_K;                       // 32-column K-chunks per layer (8 KB of A operand each)
   constexpr int P_EPI_WARPS = EW;
   constexpr int P_IDS_WARP = EW + 1, P_FIRST_PROD_WARP = EW + 2;
   constexpr int P_THREADS = p_threads(NG, EW);
@@ -225,19 +230,18 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
   constexpr uint32_t IDESC = umma_idesc_f16(2 * TC_BM, H);
   // ALL shared memory is dynamic and laid out by hand (no alignment pad: the window itself is 1 KB
   // aligned — checked below — and every swizzled region starts at a multiple of 1 KB).  With H = 256
-  // and two hidden layers the resident weights take 128 KB; the rest is two rings: `ring` stages of
-  // the first layer's A operand (8 KB each, as many as fit) and P_A2_SLOTS K-blocks of activations.
+  // and two hidden layers the resident weights take 128 KB; the rest is the ring of the first layer's
+  // A operand: `ring` stages (as many as fit, 10 at H = 256) of one 8 KB K-chunk (128 rows x 32 K, SWIZZLE_64B).
+  // The later layers take their A operand from TENSOR memory (see the epilogue), not from here.
   extern __shared__ __align__(1024) uint8_t smem[];
   const int nhidden = L - 1;
   uint8_t *sW = smem;                                                   // [nhidden][WH_BYTES]
   uint8_t *sRing = sW + (size_t)nhidden * WH_BYTES;                     // [ring][8 KB]
-  uint8_t *sA2 = sRing + (size_t)ring * P_STAGE_BYTES;                  // [P_A2_SLOTS][16 KB] (nhidden >= 2)
-  uint8_t *sOnes = sA2 + (nhidden >= 2 ? P_A2_SLOTS * A2_SLOT_BYTES : 0);   // [128][16] fp16: A of the bias K-step
+  uint8_t *sOnes = sRing + (size_t)ring * P_STAGE_BYTES;                // [128][16] fp16: A of the bias K-step
   uint8_t *sBiasB = sOnes + TC_BM * 32;                                 // [nhidden][HH][16] fp16: B of the bias K-step
   float *sWlast = reinterpret_cast<float *>(sBiasB + (size_t)nhidden * HH * 32);   // [H]
   int2 *sIds = reinterpret_cast<int2 *>(sWlast + H);                    // [2][128] (u, v) of this CTA's rows
-  float *sPart = reinterpret_cast<float *>(sIds + 2 * TC_BM);           // [2][128] output-layer partial sums (EW = 8)
-  PipeBarriers &bars = *reinterpret_cast<PipeBarriers *>(sPart + 2 * TC_BM);
+  PipeBarriers &bars = *reinterpret_cast<PipeBarriers *>(sIds + 2 * TC_BM);
   cg::cluster_group cluster = cg::this_cluster();
   const uint32_t cta_rank = cluster.block_rank();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -258,10 +262,7 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
       mbar_init(smem_u32(&bars.acc_full[i]), 1);
       mbar_init(smem_u32(&bars.acc_free[i]), 2 * P_EPI_WARPS);
     }
-    for (int i = 0; i < P_A2_SLOTS; ++i) {
-      mbar_init(smem_u32(&bars.a2_full[i]), 2 * P_EPI_WARPS);
-      mbar_init(smem_u32(&bars.a2_empty[i]), 1);
-    }
+    for (int i = 0; i < P_MAX_CHUNKS; ++i) mbar_init(smem_u32(&bars.a2_full[i]), 2 * P_EPI_WARPS);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars.ids_full[i]), 1);
       mbar_init(smem_u32(&bars.ids_empty[i]), P_PROD_WARPS);
@@ -304,229 +305,74 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
 
   const long long npair_tiles = (M + 2 * TC_BM - 1) / (2 * TC_BM);
   const long long nclusters = gridDim.x / 2, cluster_id = blockIdx.x / 2;
-  const int G = (tune & 2) ? 2 : 1;       // tiles per issue group (see the MMA issuer)
 
   if (warp < P_EPI_WARPS) {
-   if constexpr (EW == 8) {
-    // =============================== EPILOGUE, two warps per TMEM lane quarter ===============================
-    // Draining a 128 x H fp32 accumulator through tcgen05.ld costs about as long as the GEMM that filled it,
-    // and the next layer's MMAs wait for its K-blocks: with one warp per lane quarter a 64-column K-block took
-    // ~790 clocks against 512 for the MMAs that consume it (profiles/round1_c_tc3_timeline.md).  Here warps q
-    // and q + 4 share the rows of quarter q and split every K-block's columns (32 each), so a quarter always has
-    // a tcgen05.ld in flight while the other warp converts.  Hidden layers: cvt.rn.relu.f16x2 + swizzled
-    // 128-bit stores (the bias is already in the accumulator); output layer: each warp dots its 128 columns,
-    // the halves meet in shared memory (one 64-thread named barrier per quarter).
-    constexpr int NL = 2 * NKB;                     // 16-column loads per warp and accumulator
-    TR_DECL(1);
-    uint32_t acph = 0, a2g = 0, seq = 0, fin = 0;
-    const int q = warp & 3, hf = warp >> 2;
-    const int row = q * 32 + lane;
-    for (long long tile0 = cluster_id; tile0 < npair_tiles; tile0 += G * nclusters) {
-      const int nj = (G == 2 && tile0 + nclusters < npair_tiles) ? 2 : 1;
-      for (int l = 0; l < nhidden; ++l)
-      for (int tj = 0; tj < nj; ++tj) {
-        const long long sched = tile0 + tj * nclusters;
-        const long long p0 = (tile_order ? (long long)__ldg(tile_order + sched) : sched) * (2 * TC_BM) +
-                             (long long)cta_rank * TC_BM;
-        const uint32_t slot = G == 2 ? (uint32_t)tj : (seq++ & 1u);
-        mbar_wait_cluster(smem_u32(&bars.acc_full[slot]), (acph >> slot) & 1u);
-        acph ^= 1u << slot;
-        tc_fence_after();
-        if (tid == 0) TR(5, l, tj);
-        // this warp's columns of the accumulator: 64 kb + 32 hf + [0, 32), kb < NKB, as NL loads of 16
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * H + (uint32_t)hf * 32u;
-        uint32_t buf[2][16];
-        tmem_ld16_issue(taddr, buf[0]);
-        if (l < nhidden - 1) {
-          uint4 hold[4];
-#pragma unroll
-          for (int kb = 0; kb < NKB; ++kb) {
-            const bool last_kb = kb == NKB - 1;       // held in registers: see the one-warp-per-quarter path below
-            uint8_t *dstrow = nullptr;
-            uint32_t a2s = 0;
-            if (!last_kb) {
-              a2s = a2g % P_A2_SLOTS;
-              mbar_wait_cluster(smem_u32(&bars.a2_empty[a2s]), ((a2g / P_A2_SLOTS) & 1u) ^ 1u);
-              dstrow = sA2 + a2s * A2_SLOT_BYTES + row * 128;
-            }
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              const int li = kb * 2 + half;
-              tmem_ld_wait16(buf[li & 1]);
-              if (li + 1 < NL)
-                tmem_ld16_issue(taddr + (uint32_t)(((li + 1) >> 1) * 64 + ((li + 1) & 1) * 16), buf[(li + 1) & 1]);
-              const uint32_t *v = buf[li & 1];
-#pragma unroll
-              for (int j = 0; j < 16; j += 8) {
-                uint4 o;
-                o.x = cvt_relu_f16x2(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
-                o.y = cvt_relu_f16x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                o.z = cvt_relu_f16x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
-                o.w = cvt_relu_f16x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
-                const int sub = half * 2 + (j >> 3);               // 16-byte unit inside this warp's 64 bytes
-                if (last_kb) hold[sub] = o;
-                else *reinterpret_cast<uint4 *>(dstrow + (((hf * 4 + sub) ^ (row & 7)) << 4)) = o;
-              }
-            }
-            if (!last_kb) {
-              fence_async_smem();
-              __syncwarp();
-              if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.a2_full[a2s]), 0);
-              if (tid == 0) TR(6, kb, tj);
-              ++a2g;
-            }
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.acc_free[slot]), 0);
-          if (tid == 0) TR(7, l, tj);
-          const uint32_t a2s = a2g % P_A2_SLOTS;
-          mbar_wait_cluster(smem_u32(&bars.a2_empty[a2s]), ((a2g / P_A2_SLOTS) & 1u) ^ 1u);
-          uint8_t *dstrow = sA2 + a2s * A2_SLOT_BYTES + row * 128;
-#pragma unroll
-          for (int sub = 0; sub < 4; ++sub)
-            *reinterpret_cast<uint4 *>(dstrow + (((hf * 4 + sub) ^ (row & 7)) << 4)) = hold[sub];
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.a2_full[a2s]), 0);
-          if (tid == 0) TR(6, NKB - 1, tj);
-          ++a2g;
-        } else {
-          const float4 *w4 = reinterpret_cast<const float4 *>(sWlast);
-          float2 part = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int li = 0; li < NL; ++li) {
-            tmem_ld_wait16(buf[li & 1]);
-            if (li + 1 < NL)
-              tmem_ld16_issue(taddr + (uint32_t)(((li + 1) >> 1) * 64 + ((li + 1) & 1) * 16), buf[(li + 1) & 1]);
-            const uint32_t *v = buf[li & 1];
-            const int cbase = (li >> 1) * 64 + hf * 32 + (li & 1) * 16;
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 wa = w4[(cbase + j) >> 2];
-              float2 t0 = make_float2(fmaxf(__uint_as_float(v[j + 0]), 0.f), fmaxf(__uint_as_float(v[j + 1]), 0.f));
-              float2 t1 = make_float2(fmaxf(__uint_as_float(v[j + 2]), 0.f), fmaxf(__uint_as_float(v[j + 3]), 0.f));
-              part = fma_f32x2(t0, make_float2(wa.x, wa.y), part);
-              part = fma_f32x2(t1, make_float2(wa.z, wa.w), part);
-            }
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.acc_free[slot]), 0);
-          if (tid == 0) TR(7, l, tj);
-          // the two column halves of a row meet in shared memory; the buffer alternates per output tile, and the
-          // barrier of the NEXT tile orders this tile's read before the write that reuses the buffer
-          float *sp = sPart + (fin & 1u) * TC_BM;
-          const float mine = part.x + part.y;
-          if (hf == 1) sp[row] = mine;
-          asm volatile("bar.sync %0, 64;" :: "r"(1 + q) : "memory");
-          if (hf == 0 && p0 + row < M) {
-            const float sc = (mine + sp[row]) + b_last;
-            score[p0 + row] = apply_sigmoid ? sigmoidf_ref(sc) : sc;
-          }
-          ++fin;
-        }
-      }
-    }
-   } else {
     // =============================== EPILOGUE ===============================
-    // Thread-per-row.  The accumulator already holds W x + b (the bias K-step), so a hidden-layer
-    // element costs one half of a cvt.rn.relu.f16x2 and an eighth of a 128-bit shared store — no
-    // shared-memory reads at all; the output layer reads its H weights with warp-uniform 128-bit
-    // loads.  The next 32 columns are always in flight (tcgen05.ld) while the current 32 are converted.
-    constexpr int NCH = H / 32;
+    // Warp q drains TMEM lane quarter q, thread per accumulator row, 32 columns (one tcgen05.ld.x32) at a time with
+    // the next 32 in flight.  The accumulator already holds W x + b (the bias K-step).
+    //   hidden layer: ReLU + round to fp16 (cvt.rn.relu.f16x2: two elements per instruction) and WRITE THE CHUNK BACK
+    //       TO TENSOR MEMORY, in place: the 32 fp32 columns [32c, 32c+32) of the accumulator become the 16 packed
+    //       columns [16c, 16c+16) of the same slot (a 32-bit column = two consecutive K elements of the row), which is
+    //       the layout tcgen05.mma reads an A operand from — the next layer's MMAs take their A from there and trail
+    //       the conversion chunk by chunk (a2_full[c]).  The write position never passes the read position, so no
+    //       second buffer is needed, and the activations never touch shared memory: the shared-memory pipe — 128 B
+    //       per clock for the gather stores, both MMA operands and, before, 64 KB of activation stores + 64 KB of
+    //       A-operand reads per tile — was busy ~85 % of a tile's ideal 4,352 clocks; this takes 128 KB of 384 off it
+    //       and frees 48 KB of shared memory for the gather ring.
+    //   output layer: ReLU + H -> 1 dot with warp-uniform 128-bit weight loads + sigmoid.
     TR_DECL(1);
-    uint32_t acph = 0;            // bit s = phase parity of acc_full[s] (kept in a register)
-    uint32_t a2g = 0;             // a2g: activation K-blocks produced so far (slot = a2g % P_A2_SLOTS)
-    const int row = warp * 32 + lane;
-    // Same tile / layer / slot order as the MMA issuer (see there).
+    uint32_t acph = 0;            // bit s = phase parity of acc_full[s]
     uint32_t seq = 0;
-    for (long long tile0 = cluster_id; tile0 < npair_tiles; tile0 += G * nclusters) {
-      const int nj = (G == 2 && tile0 + nclusters < npair_tiles) ? 2 : 1;
-      for (int l = 0; l < nhidden; ++l)
-      for (int tj = 0; tj < nj; ++tj) {
-        const long long sched = tile0 + tj * nclusters;       // schedule slot -> pair tile (u-block order)
-        const long long p0 = (tile_order ? (long long)__ldg(tile_order + sched) : sched) * (2 * TC_BM) +
-                             (long long)cta_rank * TC_BM;
-        const uint32_t slot = G == 2 ? (uint32_t)tj : (seq++ & 1u);
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    for (long long tile = cluster_id; tile < npair_tiles; tile += nclusters) {
+      const long long p0 = (tile_order ? (long long)__ldg(tile_order + tile) : tile) * (2 * TC_BM) +
+                           (long long)cta_rank * TC_BM;
+      for (int l = 0; l < nhidden; ++l) {
+        const uint32_t slot = seq++ & 1u;
         mbar_wait_cluster(smem_u32(&bars.acc_full[slot]), (acph >> slot) & 1u);
         acph ^= 1u << slot;
         tc_fence_after();
-        if (tid == 0) TR(5, l, tj);
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + slot * H;
+        if (tid == 0) TR(5, l, 0);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * H;
         uint32_t buf[2][32];
         tmem_ld32_issue(taddr, buf[0]);
         if (l < nhidden - 1) {
-          // The LAST K-block of the tile is converted into registers, not stored: the accumulator slot
-          // is handed back (acc_free) as soon as every column has been read, and only then does the
-          // warp wait for a free slot of the activation ring.  The ring holds fewer K-blocks than a
-          // tile has, and the MMAs that drain it (the next layer of THIS tile) write the very slot
-          // being read here — so they must not be a precondition for finishing the read.
-          uint8_t *dstrow = nullptr;
-          uint32_t a2s = 0;
-          uint4 hold[8];
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) {
+          for (int c = 0; c < NCHUNK; ++c) {
             tmem_ld_wait(buf[c & 1]);
-            if (c + 1 < NCH) tmem_ld32_issue(taddr + (uint32_t)(c + 1) * 32u, buf[(c + 1) & 1]);
-            const bool last_kb = c >= NCH - 2;
-            if (!last_kb && (c & 1) == 0) {
-              // K-block c/2 of the next layer's A operand goes to slot a2g % 3 of the activation ring:
-              // wait until the MMAs that read the slot's previous contents have retired
-              a2s = a2g % P_A2_SLOTS;
-              mbar_wait_cluster(smem_u32(&bars.a2_empty[a2s]), ((a2g / P_A2_SLOTS) & 1u) ^ 1u);
-              dstrow = sA2 + a2s * A2_SLOT_BYTES + row * 128;
-            }
+            if (c + 1 < NCHUNK) tmem_ld32_issue(taddr + (uint32_t)(c + 1) * 32u, buf[(c + 1) & 1]);
             const uint32_t *v = buf[c & 1];
+            uint32_t o[16];
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 o;
-              o.x = cvt_relu_f16x2(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
-              o.y = cvt_relu_f16x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-              o.z = cvt_relu_f16x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
-              o.w = cvt_relu_f16x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
-              const int chunk = (c & 1) * 4 + (j >> 3);
-              if (last_kb) hold[chunk] = o;
-              else *reinterpret_cast<uint4 *>(dstrow + ((chunk ^ (row & 7)) << 4)) = o;
-            }
-            if (!last_kb && (c & 1)) {
-              // the K-block is complete: the tensor pipe starts the next layer on it while the
-              // remaining columns of this tile are still being converted
-              fence_async_smem();
-              __syncwarp();
-              if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.a2_full[a2s]), 0);
-              if (tid == 0) TR(6, c >> 1, tj);
-              ++a2g;
-            }
+            for (int j = 0; j < 16; ++j) o[j] = cvt_relu_f16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+            tmem_st16(taddr + (uint32_t)c * 16u, o);
+            tmem_st_wait();
+            // the chunk is in place: the tensor pipe starts (continues) the next layer on it while the remaining
+            // columns of this tile are still being converted
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.a2_full[c]), 0);
+            if (tid == 0) TR(6, c, 0);
           }
-          tc_fence_before();
+          // the slot is handed back as the NEXT layer's A operand; whoever overwrites it later (an MMA of a later
+          // layer / tile) is ordered behind the MMAs that read it by the tensor pipe's program order
           __syncwarp();
           if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.acc_free[slot]), 0);
-          if (tid == 0) TR(7, l, tj);
-          a2s = a2g % P_A2_SLOTS;
-          mbar_wait_cluster(smem_u32(&bars.a2_empty[a2s]), ((a2g / P_A2_SLOTS) & 1u) ^ 1u);
-          dstrow = sA2 + a2s * A2_SLOT_BYTES + row * 128;
-#pragma unroll
-          for (int chunk = 0; chunk < 8; ++chunk)
-            *reinterpret_cast<uint4 *>(dstrow + ((chunk ^ (row & 7)) << 4)) = hold[chunk];
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.a2_full[a2s]), 0);
-          if (tid == 0) TR(6, NKB - 1, tj);
-          ++a2g;
+          if (tid == 0) TR(7, l, 0);
         } else {
           const float4 *w4 = reinterpret_cast<const float4 *>(sWlast);
           float2 part = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) {
+          for (int c = 0; c < NCHUNK; ++c) {
             tmem_ld_wait(buf[c & 1]);
-            if (c + 1 < NCH) tmem_ld32_issue(taddr + (uint32_t)(c + 1) * 32u, buf[(c + 1) & 1]);
+            if (c + 1 < NCHUNK) tmem_ld32_issue(taddr + (uint32_t)(c + 1) * 32u, buf[(c + 1) & 1]);
             const uint32_t *v = buf[c & 1];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 wa = w4[(c * 32 + j) >> 2];
-              float2 t0 = make_float2(fmaxf(__uint_as_float(v[j + 0]), 0.f), fmaxf(__uint_as_float(v[j + 1]), 0.f));
-              float2 t1 = make_float2(fmaxf(__uint_as_float(v[j + 2]), 0.f), fmaxf(__uint_as_float(v[j + 3]), 0.f));
+            for (int e = 0; e < 32; e += 4) {
+              const float4 wa = w4[(c * 32 + e) >> 2];
+              float2 t0 = make_float2(fmaxf(__uint_as_float(v[e + 0]), 0.f), fmaxf(__uint_as_float(v[e + 1]), 0.f));
+              float2 t1 = make_float2(fmaxf(__uint_as_float(v[e + 2]), 0.f), fmaxf(__uint_as_float(v[e + 3]), 0.f));
               part = fma_f32x2(t0, make_float2(wa.x, wa.y), part);
               part = fma_f32x2(t1, make_float2(wa.z, wa.w), part);
             }
@@ -534,15 +380,14 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.acc_free[slot]), 0);
-          if (tid == 0) TR(7, l, tj);
+          if (tid == 0) TR(7, l, 0);
           if (p0 + row < M) {
-            const float s = (part.x + part.y) + b_last;
-            score[p0 + row] = apply_sigmoid ? sigmoidf_ref(s) : s;
+            const float sc = (part.x + part.y) + b_last;
+            score[p0 + row] = apply_sigmoid ? sigmoidf_ref(sc) : sc;
           }
         }
       }
     }
-   }
   } else if (warp == P_EPI_WARPS) {
     // =============================== MMA ISSUER (leader CTA, one lane) ===============================
     if (cta_rank == 0 && lane == 0) {   // lanes 1..31 wait at the __syncwarp below (keeps the warp
@@ -554,42 +399,36 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
       // field counts 16-byte units and never carries out of its 14 bits), ring positions and barrier
       // phases are carried incrementally (no division by the run-time ring depth).
       uint32_t afph = 0;
-      const uint64_t dRing = umma_smem_desc_sw64(smem_u32(sRing)), dA2 = umma_smem_desc(smem_u32(sA2));
+      const uint64_t dRing = umma_smem_desc_sw64(smem_u32(sRing));
       const uint64_t dW = umma_smem_desc(smem_u32(sW));
       const uint64_t dOnes = umma_smem_desc_sw32(smem_u32(sOnes)), dBias = umma_smem_desc_sw32(smem_u32(sBiasB));
       const uint32_t full0 = smem_u32(&bars.full[0]), empty0 = smem_u32(&bars.empty[0]);
-      const uint32_t a2full0 = smem_u32(&bars.a2_full[0]), a2empty0 = smem_u32(&bars.a2_empty[0]);
+      const uint32_t a2full0 = smem_u32(&bars.a2_full[0]);
       uint32_t stage = 0, stage_ph = 0;        // first-layer ring position / parity of full[stage]
-      uint32_t a2s = 0, a2_ph = 0;             // activation ring position / parity of a2_full[a2s]
-      // Issue order.  G = 1: tile by tile, the layers of a tile alternate between the two accumulator
-      // slots (layer l+1 trails the epilogue of layer l K-block by K-block, the next tile's first
-      // layer overlaps the last epilogue).  G = 2 (tune bit 1): layer by layer over a PAIR of tiles,
-      // tile j in slot j, so every dependent step has a whole GEMM of the other tile to hide behind —
-      // at the price of first-layer bursts twice as long for the gather ring to absorb.
+      uint32_t a2_ph = 0;                      // parity of a2_full[*] (each is used once per later layer)
+      // Issue order: tile by tile, the layers of a tile alternate between the two accumulator slots (layer l+1
+      // trails the epilogue of layer l chunk by chunk, the next tile's first layer overlaps the last epilogue).
       uint32_t seq = 0;
-      for (long long tile0 = cluster_id; tile0 < npair_tiles; tile0 += G * nclusters) {
-        const int nj = (G == 2 && tile0 + nclusters < npair_tiles) ? 2 : 1;
-        for (int l = 0; l < nhidden; ++l)
-        for (int tj = 0; tj < nj; ++tj) {
-          const uint32_t slot = G == 2 ? (uint32_t)tj : (seq++ & 1u);
+      for (long long tile = cluster_id; tile < npair_tiles; tile += nclusters) {
+        for (int l = 0; l < nhidden; ++l) {
+          const uint32_t slot = seq++ & 1u;
           mbar_wait_cluster(smem_u32(&bars.acc_free[slot]), ((afph >> slot) & 1u) ^ 1u);   // first use passes
           afph ^= 1u << slot;
           tc_fence_after();
-          TR(1, l, tj);
+          TR(1, l, 0);
           const uint32_t d = tmem_base + slot * H;
           // bias K-step: initialises the accumulator with b[l] in every row
           umma_f16_ss_2cta_p(d, dOnes, dBias + (uint64_t)(l * ((HH * 32) >> 4)), IDESC, 0u);
           const uint64_t dWl = dW + (uint64_t)(l * (WH_BYTES >> 4));
-          // The barrier of the NEXT stage / K-block is looked at right after the first MMA of the current
-          // one has been issued, so its round trip to shared memory runs under that MMA instead of
-          // between two of them.
+          // The barrier of the NEXT chunk is looked at right after the first MMA of the current one has been
+          // issued, so its round trip to shared memory runs under that MMA instead of between two of them.
+          uint32_t ready = 0;
           if (l == 0) {
-            uint32_t ready = 0;
 #pragma unroll
             for (int c = 0; c < NCHUNK; ++c) {
               if (!ready) mbar_wait_cluster(full0 + stage * 8u, stage_ph);
               tc_fence_after();
-              TR(2, c, tj);
+              TR(2, c, 0);
               const uint64_t ad = dRing + (uint64_t)(stage * (P_STAGE_BYTES >> 4));
               const uint32_t cur = stage;
               if (++stage == (uint32_t)ring) { stage = 0; stage_ph ^= 1u; }
@@ -600,79 +439,89 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
                                     dWl + (uint64_t)(((k >> 6) * (HH * 128) + ((k & 63) >> 4) * 32) >> 4), IDESC, 1u);
                 if (k16 == 0) ready = (c + 1 < NCHUNK) ? mbar_test(full0 + stage * 8u, stage_ph) : 0u;
               }
-              umma_commit_mc(empty0 + cur * 8u);
+              umma_commit_mc(empty0 + cur * 8u);            // stage reusable once these MMAs retire
             }
           } else {
-            uint32_t ready = 0;
+            // A operand = the previous layer's activations, fp16-packed in the OTHER accumulator slot (see the epilogue)
+            const uint32_t a_tmem = tmem_base + (slot ^ 1u) * H;
 #pragma unroll
-            for (int kb = 0; kb < NKB; ++kb) {
-              if (!ready) mbar_wait_cluster(a2full0 + a2s * 8u, a2_ph);   // K-block kb is in place
+            for (int c = 0; c < NCHUNK; ++c) {
+              if (!ready) mbar_wait_cluster(a2full0 + (uint32_t)c * 8u, a2_ph);   // chunk c has been converted
               tc_fence_after();
-              TR(3, kb, tj);
-              const uint64_t ad = dA2 + (uint64_t)(a2s * (A2_SLOT_BYTES >> 4));
-              const uint32_t cur = a2s;
-              if (++a2s == P_A2_SLOTS) { a2s = 0; a2_ph ^= 1u; }
+              TR(3, c, 0);
 #pragma unroll
-              for (int k16 = 0; k16 < 4; ++k16) {
-                umma_f16_ss_2cta_p(d, ad + (uint64_t)(k16 * 2), dWl + (uint64_t)((kb * (HH * 128) + k16 * 32) >> 4), IDESC, 1u);
-                if (k16 == 2) ready = (kb + 1 < NKB) ? mbar_test(a2full0 + a2s * 8u, a2_ph) : 0u;
+              for (int k16 = 0; k16 < P_CHUNK_K / 16; ++k16) {
+                const int k = c * P_CHUNK_K + k16 * 16;
+                umma_f16_ts_2cta_p(d, a_tmem + (uint32_t)(k >> 1),
+                                    dWl + (uint64_t)(((k >> 6) * (HH * 128) + ((k & 63) >> 4) * 32) >> 4), IDESC, 1u);
+                if (k16 == 0) ready = (c + 1 < NCHUNK) ? mbar_test(a2full0 + (uint32_t)(c + 1) * 8u, a2_ph) : 0u;
               }
-              umma_commit_mc(a2empty0 + cur * 8u);      // slot reusable once these MMAs retire
             }
+            a2_ph ^= 1u;
           }
           umma_commit_mc(smem_u32(&bars.acc_full[slot]));
-          TR(4, l, tj);
+          TR(4, l, 0);
         }
       }
     }
     __syncwarp();
   } else if (warp == P_IDS_WARP) {
-    // =============================== PAIR-ID PREFETCH ===============================
-    // one tile ahead of the producers: (u, v) of this CTA's 128 rows -> shared memory, so the row
-    // gathers never wait on a dependent index load
-    long long tl = 0;
-    for (long long tile = cluster_id; tile < npair_tiles; tile += nclusters, ++tl) {
-      const int slot = (int)(tl & 1);
-      mbar_wait_cluster(smem_u32(&bars.ids_empty[slot]), (uint32_t)(((tl >> 1) & 1) ^ 1));
+    // =============================== PAIR IDS ===============================
+    // (u, v) of this CTA's 128 rows -> shared memory, one tile ahead of the warps that gather, so a row gather never
+    // waits on a dependent index load.  The ids of the tile after that are already in registers, and their embedding
+    // rows are pulled into L2 from there (one DRAM page visit per 512-byte row instead of eight chunk-sized ones;
+    // the gathers, about one tile-time later, then hit L2).
+    constexpr int RB = H * (HB ? 2 : 4);
+    const char *hb = reinterpret_cast<const char *>(h);
+    int nu[4], nv[4];
+    auto load_ids = [&](long long tile) {
       const long long p0 = (tile_order ? (long long)__ldg(tile_order + tile) : tile) * (2 * TC_BM) +
                            (long long)cta_rank * TC_BM;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int r = lane + 32 * q;
-        int2 id = make_int2(-1, -1);
-        if (p0 + r < M) { id.x = __ldg(pu + p0 + r); id.y = __ldg(pv + p0 + r); }
-        sIds[slot * TC_BM + r] = id;
-        // pull the whole embedding rows of the NEXT tile into L2 now (one DRAM page visit per row
-        // instead of eight chunk-sized ones later); the producers' loads then hit L2
-        const int vprev = __shfl_up_sync(FULL, id.y, 1);
-        if ((tune & 1) && id.x >= 0) {
-          constexpr int RB = H * (HB ? 2 : 4);
-          const char *ru = reinterpret_cast<const char *>(h) + (size_t)id.x * RB;
+        const long long p = p0 + lane + 32 * q;
+        nu[q] = -1; nv[q] = -1;
+        if (p < M) { nu[q] = __ldg(pu + p); nv[q] = __ldg(pv + p); }
+      }
+      if (tune & 1) {
 #pragma unroll
-          for (int b = 0; b < RB; b += 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(ru + b));
-          if (lane == 0 || vprev != id.y) {                  // runs of equal v: prefetch each row once
-            const char *rv = reinterpret_cast<const char *>(h) + (size_t)id.y * RB;
+        for (int q = 0; q < 4; ++q) {
+          const int vprev = __shfl_up_sync(FULL, nv[q], 1);
+          if (nu[q] >= 0) {
+            const char *rup = hb + (size_t)nu[q] * RB;
 #pragma unroll
-            for (int b = 0; b < RB; b += 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(rv + b));
+            for (int b = 0; b < RB; b += 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(rup + b));
+            if (lane == 0 || vprev != nv[q]) {                   // runs of equal v: prefetch each row once
+              const char *rvp = hb + (size_t)nv[q] * RB;
+#pragma unroll
+              for (int b = 0; b < RB; b += 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(rvp + b));
+            }
           }
         }
       }
+    };
+    if (cluster_id < npair_tiles) load_ids(cluster_id);
+    long long tl = 0;
+    for (long long tile = cluster_id; tile < npair_tiles; tile += nclusters, ++tl) {
+      const int slot = (int)(tl & 1);
+      mbar_wait_cluster(smem_u32(&bars.ids_empty[slot]), (uint32_t)(((tl >> 1) & 1) ^ 1));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sIds[slot * TC_BM + lane + 32 * q] = make_int2(nu[q], nv[q]);
       __syncwarp();
       if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.ids_full[slot]), cta_rank);
+      if (tile + nclusters < npair_tiles) load_ids(tile + nclusters);
     }
   } else {
     // =============================== PRODUCERS ===============================
-    // Three independent groups of four warps; group g produces chunks g, g+3, g+6, ... of the
-    // flattened chunk stream of this CTA's tiles (a chunk = 128 rows x 32 K) into ring stage
-    // (chunk % ring) — more stages than groups, so a group never waits on the stage it has just filled.
+    // NG independent groups of four warps; group g produces chunks g, g+NG, g+2NG, ... of the flattened chunk
+    // stream of this CTA's tiles (a chunk = 128 rows x 32 K) in ring stage (chunk % ring).
     // Lane mapping inside a group (128 threads): 4 consecutive lanes cover one row's chunk, each lane
-    // 8 K-elements = one 16-byte unit of the swizzled stage; a warp instruction covers 8 rows, and
-    // rows that share v (the common case inside a run of the column-major candidate order) coalesce
-    // into one request.
-    //   HB (fp16 copy of h, the hot path): cp.async of the h[u] pieces straight into the ring stage, multiplied
-    //       in place by h[v] when they have landed (see issue_async / process below);
-    //   fp32 source (small pair lists, no table): 4 x LDG.128 per row into registers, one chunk in flight.
-    const int pw = warp - P_FIRST_PROD_WARP;                 // 0..11
+    // 8 K-elements = one 16-byte unit of the swizzled stage; a warp instruction covers 8 rows.
+    //   fp16 table (the hot path): the h[u] pieces are ALREADY in the stage (TMA gather4, see the ids warp); the
+    //       group multiplies them in place by h[v] — one 16-byte piece per thread and chunk, because the list is
+    //       grouped by v (a row whose v differs fetches its own piece, predicated) — and hands the stage to the MMA;
+    //   fp32 source (short pair lists, no table): 4 x LDG.128 per row into registers, rounded like the table.
+    const int pw = warp - P_FIRST_PROD_WARP;
     const int group = pw / P_GROUP_WARPS;
     const int t = (pw % P_GROUP_WARPS) * 32 + lane;          // 0..127
     const int l4 = t & 3;
@@ -682,17 +531,9 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
     const long long total = my_tiles * NCHUNK;
     const char *hbase = reinterpret_cast<const char *>(h);
     constexpr int ROW_BYTES = H * (HB ? 2 : 4);
-    constexpr int LPR = HB ? 1 : 2;                          // LDG.128 per row and operand
     long long cur_tl = -1;
     int idu[4], idv[4];
     TR_DECL(2 + group);
-    // h[v] is loaded ONCE per thread and chunk: the candidate list is grouped by v (runs of thousands
-    // of pairs), so a thread's four rows almost always share it.  A row whose v differs (a run boundary,
-    // or an arbitrary pair list) fetches its own copy when the buffer is consumed.  Besides a quarter of
-    // the L1 wavefronts this frees 12 registers per buffer, which is what lets two buffers live in the
-    // 96 registers a 576-thread CTA can have.
-    struct Buf { uint4 xu[4][LPR], xv[LPR]; int v[4]; uint32_t valid; };
-
     // Move this warp's position in the pair-id pipeline to tile `tl`: release every tile left behind
     // (also tiles this group has no chunk in — H = 64 has 2 chunks per tile for 3 groups), waiting
     // for each tile's ids to have been published first so that a release can never be counted
@@ -708,170 +549,77 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
           mbar_wait_cluster(smem_u32(&bars.ids_full[cur_tl & 1]), (uint32_t)((cur_tl >> 1) & 1));
       }
     };
-    auto issue = [&](Buf &b, long long i) {
-      const long long tl = i / NCHUNK;
-      const int c = (int)(i - tl * NCHUNK);
-      if (tl != cur_tl) {
-        advance_to(tl);
+    auto enter_tile = [&](long long tl) {
+      advance_to(tl);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int2 id = sIds[(tl & 1) * TC_BM + rg + 32 * q];
-          idu[q] = id.x; idv[q] = id.y;
-        }
+      for (int q = 0; q < 4; ++q) {
+        const int2 id = sIds[(tl & 1) * TC_BM + rg + 32 * q];
+        idu[q] = id.x; idv[q] = id.y;
       }
-      const int boff = (c * P_CHUNK_K + l4 * 8) * (HB ? 2 : 4);
-      if (t == 0) TR(8, c, group);
-      b.valid = 0;
-      if (tune & 4) {            // EXPERIMENT (EPS_TC3_TUNE bit 2): no gathers at all — the kernel's time without them
+    };
+    // ring position of this group's next chunk and the parities its barriers are waited with, carried
+    // incrementally (the group's chunks are NG apart and NG < ring: at most one wrap a step)
+    uint32_t pstage = (uint32_t)group;
+    if constexpr (HB) {
+      // fp16 table: 2 x LDG.128 per row pair -> 4 + 1 loads per thread and chunk, and the loads of the NEXT chunk are
+      // issued before the current one is multiplied (two register buffers).  h[v] is loaded ONCE per thread and chunk:
+      // the list is grouped by v (runs of thousands of pairs), so a thread's four rows almost always share it.
+      // Measured alternatives, all slower (profiles/round2_c_k2_gather.md): cp.async / TMA gather4 straight into the
+      // ring followed by an in-place multiply — the extra shared-memory read + write per element costs more than the
+      // deeper prefetch gains, the shared-memory pipe being the co-critical resource of this kernel.
+      struct Buf { uint4 xu[4], xv; int v[4]; uint32_t valid; };
+      uint32_t ephase = 1u;
+      auto issue = [&](Buf &b, long long i) {
+        const long long tl = i / NCHUNK;
+        const int c = (int)(i - tl * NCHUNK);
+        if (tl != cur_tl) enter_tile(tl);
+        const int boff = (c * P_CHUNK_K + l4 * 8) * 2;
+        if (t == 0) TR(8, c, group);
+        b.valid = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           b.v[q] = idv[q];
-          if (idu[q] >= 0) b.valid |= 1u << q;
-#pragma unroll
-          for (int j = 0; j < LPR; ++j) b.xu[q][j] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
-        }
-#pragma unroll
-        for (int j = 0; j < LPR; ++j) b.xv[j] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
-        return;
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        b.v[q] = idv[q];
-        if (idu[q] >= 0) {
-          b.valid |= 1u << q;
-          const uint4 *pu4 = reinterpret_cast<const uint4 *>(hbase + (size_t)idu[q] * ROW_BYTES + boff);
-#pragma unroll
-          for (int j = 0; j < LPR; ++j) b.xu[q][j] = __ldg(pu4 + j);
-        }
-      }
-      if (b.valid) {                                         // rows are valid from q = 0 up
-        const uint4 *pv4 = reinterpret_cast<const uint4 *>(hbase + (size_t)idv[0] * ROW_BYTES + boff);
-#pragma unroll
-        for (int j = 0; j < LPR; ++j) b.xv[j] = __ldg(pv4 + j);
-      }
-    };
-    // ring position of this group's next chunk and the parity its `empty` barrier is waited with,
-    // carried incrementally (the group's chunks are NG apart and NG < ring: at most one wrap a step)
-    uint32_t pstage = (uint32_t)group, pphase = 1u;
-    auto consume = [&](Buf &b, long long i) {
-      const uint32_t stage = pstage;
-      uint8_t *dst = sRing + stage * P_STAGE_BYTES;
-      const int boff = ((int)(i % NCHUNK) * P_CHUNK_K + l4 * 8) * (HB ? 2 : 4);
-      mbar_wait_cluster(smem_u32(&bars.empty[stage]), pphase);   // the MMAs that read this stage retired
-      pstage += NG;
-      if (pstage >= (uint32_t)ring) { pstage -= (uint32_t)ring; pphase ^= 1u; }
-      if (t == 0) TR(9, (int)(i % NCHUNK), group);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int r = rg + 32 * q;
-        uint4 o = make_uint4(0u, 0u, 0u, 0u);
-        if ((b.valid >> q) & 1u) {
-          uint4 xv[LPR];
-#pragma unroll
-          for (int j = 0; j < LPR; ++j) xv[j] = b.xv[j];
-          if (q > 0) {
-            // A row whose v differs from the buffer's (a run boundary, or an arbitrary pair list) fetches its own
-            // copy — as a PREDICATED load.  Written as `if (v[q] != v[0]) xv = __ldg(..)` the compiler turned it
-            // into an UNCONDITIONAL load from a selected address (round-2 SASS: three dependent LDG.E.128 per
-            // chunk in front of the HMUL2s), i.e. every chunk waited for three serial L1/L2 round trips and the
-            // first layer ran at half the tensor pipe's pace (profiles/round2_b_tc_timeline.md).
-            const uint4 *pv4 = reinterpret_cast<const uint4 *>(hbase + (size_t)b.v[q] * ROW_BYTES + boff);
-#pragma unroll
-            for (int j = 0; j < LPR; ++j)
-              asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, %6;\n\t"
-                           "@p ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}\n"
-                           : "+r"(xv[j].x), "+r"(xv[j].y), "+r"(xv[j].z), "+r"(xv[j].w)
-                           : "l"(pv4 + j), "r"(b.v[q]), "r"(b.v[0]));
-          }
-          if (HB) {
-            o.x = mul_f16x2(b.xu[q][0].x, xv[0].x); o.y = mul_f16x2(b.xu[q][0].y, xv[0].y);
-            o.z = mul_f16x2(b.xu[q][0].z, xv[0].z); o.w = mul_f16x2(b.xu[q][0].w, xv[0].w);
-          } else {
-            const uint4 a0 = b.xu[q][0], a1 = b.xu[q][LPR - 1], c0 = xv[0], c1 = xv[LPR - 1];
-            o.x = hadamard_f16x2(__uint_as_float(a0.x), __uint_as_float(a0.y), __uint_as_float(c0.x), __uint_as_float(c0.y), hscale);
-            o.y = hadamard_f16x2(__uint_as_float(a0.z), __uint_as_float(a0.w), __uint_as_float(c0.z), __uint_as_float(c0.w), hscale);
-            o.z = hadamard_f16x2(__uint_as_float(a1.x), __uint_as_float(a1.y), __uint_as_float(c1.x), __uint_as_float(c1.y), hscale);
-            o.w = hadamard_f16x2(__uint_as_float(a1.z), __uint_as_float(a1.w), __uint_as_float(c1.z), __uint_as_float(c1.w), hscale);
+          if (idu[q] >= 0) {
+            b.valid |= 1u << q;
+            b.xu[q] = __ldg(reinterpret_cast<const uint4 *>(hbase + (size_t)idu[q] * ROW_BYTES + boff));
           }
         }
-        *reinterpret_cast<uint4 *>(dst + sw64_chunk_off(r, l4)) = o;
-      }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.full[stage]), 0);
-      if (t == 0) TR(10, (int)(i % NCHUNK), group);
-    };
-
-    // ---- fp16-table path: the gathered rows land IN the ring stage (cp.async, 16 B per row and thread, already at
-    // their swizzled position) and are multiplied by h[v] in place once they have arrived.  cp.async groups are
-    // waited for by AGE (wait_group 1 = everything but the newest), so the rows of the next chunk stay in flight
-    // while the current chunk is multiplied — with register buffers the first use of a buffer also waited for the
-    // loads issued after it (one scoreboard), and the first layer ran at ~550 clocks per chunk for 256 clocks of
-    // MMA work (profiles/round2_b_tc_timeline.md).  Nothing but the 16-byte h[v] piece lives in registers.
-    struct St { int v[4]; uint32_t valid, stage; int boff; uint4 xv; };
-    auto issue_async = [&](St &st, long long i) {
-      const long long tl = i / NCHUNK;
-      const int c = (int)(i - tl * NCHUNK);
-      if (tl != cur_tl) {
-        advance_to(tl);
+        if (b.valid) b.xv = __ldg(reinterpret_cast<const uint4 *>(hbase + (size_t)idv[0] * ROW_BYTES + boff));   // rows are valid from q = 0 up
+      };
+      auto consume = [&](Buf &b, long long i) {
+        const uint32_t stage = pstage;
+        uint8_t *dst = sRing + stage * P_STAGE_BYTES;
+        const int c = (int)(i % NCHUNK);
+        const int boff = (c * P_CHUNK_K + l4 * 8) * 2;
+        mbar_wait_cluster(smem_u32(&bars.empty[stage]), ephase);   // the MMAs that read this stage retired
+        pstage += NG;
+        if (pstage >= (uint32_t)ring) { pstage -= (uint32_t)ring; ephase ^= 1u; }
+        if (t == 0) TR(9, c, group);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int2 id = sIds[(tl & 1) * TC_BM + rg + 32 * q];
-          idu[q] = id.x; idv[q] = id.y;
+          uint4 o = make_uint4(0u, 0u, 0u, 0u);
+          if ((b.valid >> q) & 1u) {
+            uint4 xv = b.xv;
+            if (q > 0) {
+              // A row of another owner (run boundary, arbitrary pair list) fetches its own h[v] piece — as a PREDICATED
+              // load: written as `if (v[q] != v[0]) xv = __ldg(..)` the compiler emits an unconditional load from a
+              // selected address, i.e. three dependent L1/L2 round trips per chunk in front of the HMUL2s.
+              const uint4 *pv4 = reinterpret_cast<const uint4 *>(hbase + (size_t)b.v[q] * ROW_BYTES + boff);
+              asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, %6;\n\t"
+                           "@p ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}\n"
+                           : "+r"(xv.x), "+r"(xv.y), "+r"(xv.z), "+r"(xv.w) : "l"(pv4), "r"(b.v[q]), "r"(b.v[0]));
+            }
+            o.x = mul_f16x2(b.xu[q].x, xv.x); o.y = mul_f16x2(b.xu[q].y, xv.y);
+            o.z = mul_f16x2(b.xu[q].z, xv.z); o.w = mul_f16x2(b.xu[q].w, xv.w);
+          }
+          *reinterpret_cast<uint4 *>(dst + sw64_chunk_off(rg + 32 * q, l4)) = o;
         }
-      }
-      const uint32_t stage = pstage;
-      mbar_wait_cluster(smem_u32(&bars.empty[stage]), pphase);   // the MMAs that read this stage retired
-      pstage += NG;
-      if (pstage >= (uint32_t)ring) { pstage -= (uint32_t)ring; pphase ^= 1u; }
-      if (t == 0) TR(8, c, group);
-      st.stage = stage;
-      st.boff = (c * P_CHUNK_K + l4 * 8) * 2;
-      st.valid = 0;
-      const uint32_t dst0 = smem_u32(sRing + stage * P_STAGE_BYTES);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        st.v[q] = idv[q];
-        const bool ok = idu[q] >= 0;
-        if (ok) st.valid |= 1u << q;
-        const char *src = hbase + (ok ? (size_t)idu[q] * ROW_BYTES + st.boff : (size_t)0);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
-                     :: "r"(dst0 + sw64_chunk_off(rg + 32 * q, l4)), "l"(src), "r"(ok ? 16 : 0) : "memory");   // 0: zero fill
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      st.xv = make_uint4(0u, 0u, 0u, 0u);
-      if (st.valid) st.xv = __ldg(reinterpret_cast<const uint4 *>(hbase + (size_t)idv[0] * ROW_BYTES + st.boff));
-    };
-    auto process = [&](St &st, bool newer_in_flight) {
-      if (newer_in_flight) asm volatile("cp.async.wait_group 1;" ::: "memory");
-      else asm volatile("cp.async.wait_group 0;" ::: "memory");
-      if (t == 0) TR(9, (int)(st.boff >> 6), group);
-      uint8_t *dst = sRing + st.stage * P_STAGE_BYTES;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint4 *cell = reinterpret_cast<uint4 *>(dst + sw64_chunk_off(rg + 32 * q, l4));
-        const uint4 xu = *cell;
-        uint4 xv = st.xv;
-        if (q > 0) {          // a row of another owner (run boundary, arbitrary pair list) fetches its own h[v] piece
-          const uint4 *pv4 = reinterpret_cast<const uint4 *>(hbase + (size_t)st.v[q] * ROW_BYTES + st.boff);
-          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, %6;\n\t"
-                       "@p ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}\n"
-                       : "+r"(xv.x), "+r"(xv.y), "+r"(xv.z), "+r"(xv.w) : "l"(pv4), "r"(st.v[q]), "r"(st.v[0]));
-        }
-        uint4 o;
-        o.x = mul_f16x2(xu.x, xv.x); o.y = mul_f16x2(xu.y, xv.y);
-        o.z = mul_f16x2(xu.z, xv.z); o.w = mul_f16x2(xu.w, xv.w);
-        if (!((st.valid >> q) & 1u)) o = make_uint4(0u, 0u, 0u, 0u);
-        *cell = o;
-      }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.full[st.stage]), 0);
-      if (t == 0) TR(10, (int)(st.boff >> 6), group);
-    };
-
-    long long i = group;
-    if (HB && (tune & 8)) {               // EPS_TC3_TUNE bit 3: register double buffer (A/B against cp.async below)
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.full[stage]), 0);
+        if (t == 0) TR(10, c, group);
+      };
+      long long i = group;
       Buf A, B;
       if (i < total) issue(A, i);
       while (i < total) {
@@ -883,23 +631,52 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
         consume(B, i);
         i += NG;
       }
-    } else if (HB) {
-      St A, B;
-      if (i < total) issue_async(A, i);
-      while (i < total) {
-        bool nxt = i + NG < total;
-        if (nxt) issue_async(B, i + NG);
-        process(A, nxt);
-        i += NG;
-        if (i >= total) break;
-        nxt = i + NG < total;
-        if (nxt) issue_async(A, i + NG);
-        process(B, nxt);
-        i += NG;
-      }
     } else {
-      Buf A;
-      for (; i < total; i += NG) { issue(A, i); consume(A, i); }
+      uint32_t ephase = 1u;
+      for (long long i = group; i < total; i += NG) {
+        const long long tl = i / NCHUNK;
+        const int c = (int)(i - tl * NCHUNK);
+        if (tl != cur_tl) enter_tile(tl);
+        const int boff = (c * P_CHUNK_K + l4 * 8) * 4;
+        uint4 xu[4][2], xv[2];
+        xv[0] = xv[1] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          xu[q][0] = xu[q][1] = make_uint4(0u, 0u, 0u, 0u);
+          if (idu[q] >= 0) {
+            const uint4 *pu4 = reinterpret_cast<const uint4 *>(hbase + (size_t)idu[q] * ROW_BYTES + boff);
+            xu[q][0] = __ldg(pu4); xu[q][1] = __ldg(pu4 + 1);
+          }
+        }
+        if (idu[0] >= 0) {
+          const uint4 *pv4 = reinterpret_cast<const uint4 *>(hbase + (size_t)idv[0] * ROW_BYTES + boff);
+          xv[0] = __ldg(pv4); xv[1] = __ldg(pv4 + 1);
+        }
+        const uint32_t stage = pstage;
+        mbar_wait_cluster(smem_u32(&bars.empty[stage]), ephase);   // the MMAs that read this stage retired
+        pstage += NG;
+        if (pstage >= (uint32_t)ring) { pstage -= (uint32_t)ring; ephase ^= 1u; }
+        uint8_t *dst = sRing + stage * P_STAGE_BYTES;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 c0 = xv[0], c1 = xv[1];
+          if (q > 0 && idu[q] >= 0 && idv[q] != idv[0]) {
+            const uint4 *pv4 = reinterpret_cast<const uint4 *>(hbase + (size_t)idv[q] * ROW_BYTES + boff);
+            c0 = __ldg(pv4); c1 = __ldg(pv4 + 1);
+          }
+          const uint4 a0 = xu[q][0], a1 = xu[q][1];
+          uint4 o;
+          o.x = hadamard_f16x2(__uint_as_float(a0.x), __uint_as_float(a0.y), __uint_as_float(c0.x), __uint_as_float(c0.y), hscale);
+          o.y = hadamard_f16x2(__uint_as_float(a0.z), __uint_as_float(a0.w), __uint_as_float(c0.z), __uint_as_float(c0.w), hscale);
+          o.z = hadamard_f16x2(__uint_as_float(a1.x), __uint_as_float(a1.y), __uint_as_float(c1.x), __uint_as_float(c1.y), hscale);
+          o.w = hadamard_f16x2(__uint_as_float(a1.z), __uint_as_float(a1.w), __uint_as_float(c1.z), __uint_as_float(c1.w), hscale);
+          if (idu[q] < 0) o = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4 *>(dst + sw64_chunk_off(rg + 32 * q, l4)) = o;
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.full[stage]), 0);
+      }
     }
     advance_to(my_tiles);                                    // release the tiles this group had no chunk in
   }
@@ -973,10 +750,9 @@ static int tc3_launch_g(const void *h, const int *pu, const int *pv, long long M
                         int apply_sigmoid, float *score, uint8_t *img, int n, int *tile_order, const TcScale *scale,
                         cudaStream_t stream) {
   const int nhidden = L - 1;
-  const size_t fixed = (size_t)nhidden * (H / 2) * H * 2 + (nhidden >= 2 ? (size_t)P_A2_SLOTS * TC_BM * 128 : 0) +
+  const size_t fixed = (size_t)nhidden * (H / 2) * H * 2 +
                        (size_t)TC_BM * 32 + (size_t)nhidden * (H / 2) * 32 +          // bias K-step tiles
-                       sizeof(float) * (size_t)H + 2 * TC_BM * sizeof(int2) + 2 * TC_BM * sizeof(float) +
-                       sizeof(PipeBarriers);
+                       sizeof(float) * (size_t)H + 2 * TC_BM * sizeof(int2) + sizeof(PipeBarriers);
   const size_t budget = 227 * 1024;
   if (fixed + (size_t)(NG + 1) * P_STAGE_BYTES > budget) return EPS_ERR_UNSUPPORTED;   // the resident weights do not fit (H = 256, L >= 4)
   int ring = (int)std::min<size_t>((budget - fixed) / P_STAGE_BYTES, (size_t)P_MAX_RING);
@@ -987,8 +763,8 @@ static int tc3_launch_g(const void *h, const int *pu, const int *pv, long long M
   EPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long npair_tiles = (M + 2 * TC_BM - 1) / (2 * TC_BM);
   const int clusters = (int)std::min<long long>(npair_tiles, (long long)(sm_count() / 2));
-  const char *tn = getenv("EPS_TC3_TUNE");   // bit0: L2 row prefetch by the id warp (default on)
-  const int tune = tn ? atoi(tn) : 9;   // bit3: register double buffer (measured faster than cp.async into a 4-stage ring: 8.56 vs 10.02 ms, gpurun_out/r2i_k2.log)
+  const char *tn = getenv("EPS_TC3_TUNE");   // bit0: L2 row prefetch by the id warp (fp32-source path; default on)
+  const int tune = tn ? atoi(tn) : 1;
   const int block_nodes = tile_order ? tc3_ublock_nodes(n, H * (HB ? 2 : 4), M) : 0;
   if (block_nodes > 0) {
     const int nblocks = (n + block_nodes - 1) / block_nodes;
@@ -1015,16 +791,11 @@ template <int H, bool HB>
 static int tc3_launch_h(const void *h, const int *pu, const int *pv, long long M, const MlpParams &prm, int L,
                         int apply_sigmoid, float *score, uint8_t *img, int n, int *tile_order, const TcScale *scale,
                         cudaStream_t stream) {
-  // producer groups: 2 (default) or 3 (EPS_TC3_GROUPS=3); epilogue warps: 4 (default: 14 warps -> 128 registers)
-  // or 8 = two per TMEM lane quarter (EPS_TC3_EPI=8: 18 warps -> 96 registers).  Measured on the ppa-like list of
-  // tools/k2_bench.py (profiles/round2_k2_epilogue_ab.md): 7.57 ms with 4, 7.74 ms with 8 — the drain of an
-  // accumulator is paced by the TMEM read path of a lane quarter, not by the warp that issues the loads.
+  // producer groups: 2 (default: 14 warps -> 128 registers) or 3 (EPS_TC3_GROUPS=3: 18 warps -> 96 registers).
+  // A second epilogue warp per TMEM lane quarter was measured and dropped (profiles/round2_k2_epilogue_ab.md).
   const char *g = getenv("EPS_TC3_GROUPS");
-  const char *e = getenv("EPS_TC3_EPI");
   if (g && g[0] == '3')
     return tc3_launch_g<H, HB, 3, 4>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, n, tile_order, scale, stream);
-  if (e && e[0] == '8')
-    return tc3_launch_g<H, HB, 2, 8>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, n, tile_order, scale, stream);
   return tc3_launch_g<H, HB, 2, 4>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, n, tile_order, scale, stream);
 }
 
