@@ -37,14 +37,16 @@ namespace eps {
 namespace cg = cooperative_groups;
 
 constexpr int P_MAX_RING = 10;                                     // first-layer ring stages (8 KB each), chosen at launch
+constexpr int P_VROWS = 4;                                         // distinct owners of a 128-row tile whose h[v] row is staged
 constexpr int P_MAX_CHUNKS = 8;                                    // 32-column K-chunks per layer at H = 256
 constexpr int P_GROUP_WARPS = 4;                                   // warps per producer group
 // Warp roles: EW epilogue warps (4, or 8 = two per TMEM lane quarter, see the epilogue), then the MMA warp,
 // the pair-id warp and NG producer groups of four warps each.
 // one CTA per SM: the whole register file is there to be used
 // (16384 registers per SM sub-partition, warps dealt round-robin: 18 warps -> 5 on one -> 96; 14 -> 4 -> 128)
-constexpr int p_threads(int ng, int ew) { return (ew + 2 + ng * P_GROUP_WARPS) * 32; }
-constexpr int p_maxreg(int ng, int ew) { return (16384 / (((p_threads(ng, ew) / 32) + 3) / 4) / 32) / 8 * 8; }
+constexpr int P_EPI_WARPS = 4;                                     // one per TMEM lane quarter
+constexpr int p_threads(int ng, int nl) { return (P_EPI_WARPS + 2 + nl + ng * P_GROUP_WARPS) * 32; }
+constexpr int p_maxreg(int ng, int nl) { return (16384 / (((p_threads(ng, nl) / 32) + 3) / 4) / 32) / 8 * 8; }
 constexpr int P_CHUNK_K = 32;
 constexpr int P_STAGE_BYTES = TC_BM * P_CHUNK_K * 2;               // 8 KB
 
@@ -187,7 +189,8 @@ __device__ __forceinline__ uint32_t mbar_test(uint32_t saddr, uint32_t parity) {
 
 struct PipeBarriers {
   uint64_t full[P_MAX_RING];   // producers (both CTAs) -> MMA issuer       (waited in the leader)
-  uint64_t empty[P_MAX_RING];  // MMA commit -> producers                    (multicast, both CTAs)
+  uint64_t empty[P_MAX_RING];  // MMA commit -> whoever refills the stage    (multicast, both CTAs)
+  uint64_t landed[P_MAX_RING]; // loader warps' copies (cp.async completion) -> producers   (CTA-local; fp16-table path)
   uint64_t acc_full[2];        // MMA commit -> epilogue                     (multicast, both CTAs)
   uint64_t acc_free[2];        // epilogue (both CTAs) -> MMA issuer         (waited in the leader)
   uint64_t a2_full[P_MAX_CHUNKS];  // epilogue (both CTAs) -> MMA issuer: 32-column chunk c of the activations is in TMEM
@@ -211,20 +214,19 @@ __device__ __forceinline__ float2 fma_f32x2(float2 a, float2 b, float2 c) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(pr));
   return r;
 }
-template <int H, bool HB /* h is the fp16 table (else fp32) */, int NG /* producer groups */, int EW /* epilogue warps */>
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(p_maxreg(NG, EW))
+template <int H, bool HB /* h is the fp16 table (else fp32) */, int NG /* producer groups */, int NL /* loader warps (fp16 table) */>
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(p_maxreg(NG, NL))
 linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, const int *__restrict__ pv,
                     long long M, const MlpParams prm, int L, int apply_sigmoid,
                     const uint8_t *__restrict__ wimg, float *__restrict__ score, int tune, int ring,
                     const int *__restrict__ tile_order, const TcScale *__restrict__ scale) {
   static_assert(H % 64 == 0 && H >= 64 && H <= 256, "H in {64,128,192,256}");
-  static_assert(EW == 4, "one epilogue warp per TMEM lane quarter (the in-place conversion relies on program order per lane)");
+  static_assert(HB ? (NL == 4 || NL == 8) : NL == 0, "loader warps exist on the fp16-table path only");
   constexpr int HH = H / 2;
   constexpr int WH_BYTES = HH * H * 2;
   constexpr int NCHUNK = H / P_CHUNK_K;                       // 32-column K-chunks per layer (8 KB of A operand each)
-  constexpr int P_EPI_WARPS = EW;
-  constexpr int P_IDS_WARP = EW + 1, P_FIRST_PROD_WARP = EW + 2;
-  constexpr int P_THREADS = p_threads(NG, EW);
+  constexpr int P_IDS_WARP = P_EPI_WARPS + 1, P_FIRST_LOAD_WARP = P_EPI_WARPS + 2, P_FIRST_PROD_WARP = P_FIRST_LOAD_WARP + NL;
+  constexpr int P_THREADS = p_threads(NG, NL);
   constexpr int P_PROD_WARPS = NG * P_GROUP_WARPS;
   constexpr uint32_t TMEM_COLS = 2 * H <= 128 ? 128 : (2 * H <= 256 ? 256 : 512);
   constexpr uint32_t IDESC = umma_idesc_f16(2 * TC_BM, H);
@@ -241,7 +243,10 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
   uint8_t *sBiasB = sOnes + TC_BM * 32;                                 // [nhidden][HH][16] fp16: B of the bias K-step
   float *sWlast = reinterpret_cast<float *>(sBiasB + (size_t)nhidden * HH * 32);   // [H]
   int2 *sIds = reinterpret_cast<int2 *>(sWlast + H);                    // [2][128] (u, v) of this CTA's rows
-  PipeBarriers &bars = *reinterpret_cast<PipeBarriers *>(sIds + 2 * TC_BM);
+  int *sKi = reinterpret_cast<int *>(sIds + 2 * TC_BM);                 // [2][128] index of the row's v in sV (-1: not cached)
+  uint8_t *sV = reinterpret_cast<uint8_t *>(sKi + 2 * TC_BM);           // [2][P_VROWS][H] fp16: h[v] rows of the tile's owners
+  int *sVid = reinterpret_cast<int *>(sV + (HB ? 2 * P_VROWS * H * 2 : 0));   // [P_VROWS] scratch of the ids warp
+  PipeBarriers &bars = *reinterpret_cast<PipeBarriers *>(sVid + 8);
   cg::cluster_group cluster = cg::this_cluster();
   const uint32_t cta_rank = cluster.block_rank();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -257,6 +262,7 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
     for (int i = 0; i < P_MAX_RING; ++i) {
       mbar_init(smem_u32(&bars.full[i]), 2 * P_GROUP_WARPS);
       mbar_init(smem_u32(&bars.empty[i]), 1);
+      mbar_init(smem_u32(&bars.landed[i]), NL > 0 ? NL * 32 : 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars.acc_full[i]), 1);
@@ -265,7 +271,7 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
     for (int i = 0; i < P_MAX_CHUNKS; ++i) mbar_init(smem_u32(&bars.a2_full[i]), 2 * P_EPI_WARPS);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars.ids_full[i]), 1);
-      mbar_init(smem_u32(&bars.ids_empty[i]), P_PROD_WARPS);
+      mbar_init(smem_u32(&bars.ids_empty[i]), P_PROD_WARPS + NL);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -507,10 +513,94 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
       mbar_wait_cluster(smem_u32(&bars.ids_empty[slot]), (uint32_t)(((tl >> 1) & 1) ^ 1));
 #pragma unroll
       for (int q = 0; q < 4; ++q) sIds[slot * TC_BM + lane + 32 * q] = make_int2(nu[q], nv[q]);
-      __syncwarp();
-      if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.ids_full[slot]), cta_rank);
-      if (tile + nclusters < npair_tiles) load_ids(tile + nclusters);
+      if constexpr (HB) {
+        // The h[v] rows of the tile's owners go to shared memory ONCE per tile (the rows are grouped by v: a tile has
+        // one owner, now and then two), so the warps that multiply never load from global memory: a register load of
+        // the h[v] piece per chunk, even an L1/L2 hit, sat in their dependency chain with 400-500 clocks
+        // (profiles/round2_d_k2_timeline.md).  Row r gets the index of its owner's row in sV, or -1 beyond P_VROWS
+        // owners (arbitrary pair lists: those rows fall back to a global load).
+        int carry = 0, last_v = -2;
+        int kq[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          int vprev = __shfl_up_sync(FULL, nv[q], 1);
+          if (lane == 0) vprev = last_v;
+          const bool flag = nu[q] >= 0 && nv[q] != vprev;
+          const unsigned bal = __ballot_sync(FULL, flag);
+          const int k = carry + __popc(bal & (0xffffffffu >> (31 - lane))) - 1;
+          if (flag && k < P_VROWS) sVid[k] = nv[q];
+          kq[q] = (nu[q] >= 0 && k >= 0 && k < P_VROWS) ? k : -1;
+          carry += __popc(bal);
+          last_v = __shfl_sync(FULL, nv[q], 31);
+        }
+        __syncwarp();
+        const int nd = min(carry, P_VROWS);
+        for (int k = 0; k < nd; ++k) {
+          if (lane < H * 2 / 16) {
+            const char *src = hb + (size_t)sVid[k] * RB + lane * 16;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                         :: "r"(smem_u32(sV + ((size_t)slot * P_VROWS + k) * (H * 2) + lane * 16)), "l"(src) : "memory");
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sKi[slot * TC_BM + lane + 32 * q] = kq[q];
+        if (tile + nclusters < npair_tiles) load_ids(tile + nclusters);     // in flight while the rows land
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.ids_full[slot]), cta_rank);
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.ids_full[slot]), cta_rank);
+        if (tile + nclusters < npair_tiles) load_ids(tile + nclusters);
+      }
     }
+  } else if (NL > 0 && warp < P_FIRST_PROD_WARP) {
+   if constexpr (NL > 0) {
+    // =============================== LOADERS (fp16 table) ===============================
+    // The gather is LATENCY bound (a 64-byte piece of a random row takes ~1,400 clocks under load), so it is done by
+    // warps that never wait for data: cp.async (LDGSTS) of the h[u] pieces of chunk j straight into ring stage
+    // j % ring, at their SWIZZLE_64B position, and the copies arrive on the stage's `landed` barrier themselves
+    // (cp.async.mbarrier.arrive.noinc).  The whole ring — all the shared memory the resident weights leave — is in
+    // flight ahead of the tensor pipe.  Dedicated warps because (a) LDGSTS bandwidth of such pieces scales with the
+    // number of issuing warps (1 warp: 2-5 B/clk, 4: 7-24, 8: 13-47; tools/micro/gather_bw.cu), and (b) the warps
+    // that MULTIPLY the landed pieces must fence.proxy.async before the MMA may read them, and that fence waits for
+    // the executing thread's own outstanding cp.async — issued by the same threads, the copies of the next chunks
+    // would be drained at every hand-off (measured: 700-1,400 clocks per chunk, profiles/round2_d_k2_timeline.md).
+    // Lane (r8 = lane / 4, l4 = lane % 4) of loader warp w copies unit l4 of rows r8 + 8 (w + NL j), j < 16 / NL.
+    constexpr int RPL = 16 / (NL > 0 ? NL : 1);
+    TR_DECL(6);
+    const int lw = warp - P_FIRST_LOAD_WARP, r8 = lane >> 2, l4 = lane & 3;
+    const char *hb = reinterpret_cast<const char *>(h);
+    long long my_tiles = 0;
+    if (cluster_id < npair_tiles) my_tiles = (npair_tiles - cluster_id + nclusters - 1) / nclusters;
+    uint32_t stage = 0, eph = 1u;                              // ring position / parity its `empty` barrier is waited with
+    for (long long tl = 0; tl < my_tiles; ++tl) {
+      const int slot = (int)(tl & 1);
+      mbar_wait_cluster(smem_u32(&bars.ids_full[slot]), (uint32_t)((tl >> 1) & 1));
+      int ru[RPL];
+#pragma unroll
+      for (int j = 0; j < RPL; ++j) ru[j] = sIds[slot * TC_BM + r8 + 8 * (lw + NL * j)].x;
+      __syncwarp();
+      if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.ids_empty[slot]), cta_rank);     // the ids are in registers
+#pragma unroll 1
+      for (int c = 0; c < NCHUNK; ++c) {
+        mbar_wait_cluster(smem_u32(&bars.empty[stage]), eph);              // the MMAs that read this stage retired
+        const uint32_t dst0 = smem_u32(sRing + stage * P_STAGE_BYTES);
+        const int boff = (c * P_CHUNK_K + l4 * 8) * 2;
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) {
+          const bool ok = ru[j] >= 0;
+          const char *src = hb + (ok ? (size_t)ru[j] * (H * 2) + boff : (size_t)0);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                       :: "r"(dst0 + sw64_chunk_off(r8 + 8 * (lw + NL * j), l4)), "l"(src), "r"(ok ? 16 : 0) : "memory");   // 0: zero fill
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(&bars.landed[stage])) : "memory");
+        if (lw == 0 && lane == 0) TR(8, c, 0);
+        if (++stage == (uint32_t)ring) { stage = 0; eph ^= 1u; }
+      }
+    }
+   }
   } else {
     // =============================== PRODUCERS ===============================
     // NG independent groups of four warps; group g produces chunks g, g+NG, g+2NG, ... of the flattened chunk
@@ -561,75 +651,66 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
     // incrementally (the group's chunks are NG apart and NG < ring: at most one wrap a step)
     uint32_t pstage = (uint32_t)group;
     if constexpr (HB) {
-      // fp16 table: 2 x LDG.128 per row pair -> 4 + 1 loads per thread and chunk, and the loads of the NEXT chunk are
-      // issued before the current one is multiplied (two register buffers).  h[v] is loaded ONCE per thread and chunk:
-      // the list is grouped by v (runs of thousands of pairs), so a thread's four rows almost always share it.
-      // Measured alternatives, all slower (profiles/round2_c_k2_gather.md): cp.async / TMA gather4 straight into the
-      // ring followed by an in-place multiply — the extra shared-memory read + write per element costs more than the
-      // deeper prefetch gains, the shared-memory pipe being the co-critical resource of this kernel.
-      struct Buf { uint4 xu[4], xv; int v[4]; uint32_t valid; };
-      uint32_t ephase = 1u;
-      auto issue = [&](Buf &b, long long i) {
+      // fp16 table: the h[u] pieces of chunk i are ALREADY in stage i % ring (the loader warps); this group multiplies
+      // them in place by h[v] — read from the tile's staged owner rows in shared memory (the ids warp), so nothing in
+      // this loop waits on global memory — and hands the stage to the MMA issuer.
+      uint32_t lphase = 0u;                                    // parity landed[pstage] is waited with
+      int kq[4] = {-1, -1, -1, -1};
+      bool uni = false;
+      const uint8_t *sVt = sV;
+      for (long long i = group; i < total; i += NG) {
         const long long tl = i / NCHUNK;
         const int c = (int)(i - tl * NCHUNK);
-        if (tl != cur_tl) enter_tile(tl);
-        const int boff = (c * P_CHUNK_K + l4 * 8) * 2;
-        if (t == 0) TR(8, c, group);
-        b.valid = 0;
+        if (tl != cur_tl) {
+          enter_tile(tl);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          b.v[q] = idv[q];
-          if (idu[q] >= 0) {
-            b.valid |= 1u << q;
-            b.xu[q] = __ldg(reinterpret_cast<const uint4 *>(hbase + (size_t)idu[q] * ROW_BYTES + boff));
-          }
+          for (int q = 0; q < 4; ++q) kq[q] = sKi[(tl & 1) * TC_BM + rg + 32 * q];
+          sVt = sV + (size_t)(tl & 1) * P_VROWS * (H * 2);
+          // rows beyond the list (u < 0) were zero-filled by the copy: 0 * anything finite = 0, they may share the path
+          uni = kq[0] >= 0;
+#pragma unroll
+          for (int q = 1; q < 4; ++q) uni = uni && (kq[q] == kq[0] || idu[q] < 0);
         }
-        if (b.valid) b.xv = __ldg(reinterpret_cast<const uint4 *>(hbase + (size_t)idv[0] * ROW_BYTES + boff));   // rows are valid from q = 0 up
-      };
-      auto consume = [&](Buf &b, long long i) {
-        const uint32_t stage = pstage;
-        uint8_t *dst = sRing + stage * P_STAGE_BYTES;
-        const int c = (int)(i % NCHUNK);
         const int boff = (c * P_CHUNK_K + l4 * 8) * 2;
-        mbar_wait_cluster(smem_u32(&bars.empty[stage]), ephase);   // the MMAs that read this stage retired
+        const uint32_t stage = pstage;
+        mbar_wait_cluster(smem_u32(&bars.landed[stage]), lphase);        // the gathered pieces have landed
         pstage += NG;
-        if (pstage >= (uint32_t)ring) { pstage -= (uint32_t)ring; ephase ^= 1u; }
+        if (pstage >= (uint32_t)ring) { pstage -= (uint32_t)ring; lphase ^= 1u; }
         if (t == 0) TR(9, c, group);
+        uint8_t *dst = sRing + stage * P_STAGE_BYTES;
+        if (uni) {
+          // the thread's four rows share one staged owner row (almost always): all five shared-memory loads are issued
+          // before the first multiply, so the chunk costs ONE load latency, not four in a row
+          const uint4 xv = *reinterpret_cast<const uint4 *>(sVt + kq[0] * (H * 2) + boff);       // warp-wide broadcast
+          uint4 xu[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 o = make_uint4(0u, 0u, 0u, 0u);
-          if ((b.valid >> q) & 1u) {
-            uint4 xv = b.xv;
-            if (q > 0) {
-              // A row of another owner (run boundary, arbitrary pair list) fetches its own h[v] piece — as a PREDICATED
-              // load: written as `if (v[q] != v[0]) xv = __ldg(..)` the compiler emits an unconditional load from a
-              // selected address, i.e. three dependent L1/L2 round trips per chunk in front of the HMUL2s.
-              const uint4 *pv4 = reinterpret_cast<const uint4 *>(hbase + (size_t)b.v[q] * ROW_BYTES + boff);
-              asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, %6;\n\t"
-                           "@p ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}\n"
-                           : "+r"(xv.x), "+r"(xv.y), "+r"(xv.z), "+r"(xv.w) : "l"(pv4), "r"(b.v[q]), "r"(b.v[0]));
-            }
-            o.x = mul_f16x2(b.xu[q].x, xv.x); o.y = mul_f16x2(b.xu[q].y, xv.y);
-            o.z = mul_f16x2(b.xu[q].z, xv.z); o.w = mul_f16x2(b.xu[q].w, xv.w);
+          for (int q = 0; q < 4; ++q) xu[q] = *reinterpret_cast<const uint4 *>(dst + sw64_chunk_off(rg + 32 * q, l4));
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            o.x = mul_f16x2(xu[q].x, xv.x); o.y = mul_f16x2(xu[q].y, xv.y);
+            o.z = mul_f16x2(xu[q].z, xv.z); o.w = mul_f16x2(xu[q].w, xv.w);
+            *reinterpret_cast<uint4 *>(dst + sw64_chunk_off(rg + 32 * q, l4)) = o;      // tail rows were zero-filled by the copy
           }
-          *reinterpret_cast<uint4 *>(dst + sw64_chunk_off(rg + 32 * q, l4)) = o;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 *cell = reinterpret_cast<uint4 *>(dst + sw64_chunk_off(rg + 32 * q, l4));
+            const uint4 xu = *cell;
+            uint4 xv;
+            if (kq[q] >= 0) xv = *reinterpret_cast<const uint4 *>(sVt + kq[q] * (H * 2) + boff);
+            else xv = __ldg(reinterpret_cast<const uint4 *>(hbase + (size_t)max(idv[q], 0) * ROW_BYTES + boff));
+            uint4 o;
+            o.x = mul_f16x2(xu.x, xv.x); o.y = mul_f16x2(xu.y, xv.y);
+            o.z = mul_f16x2(xu.z, xv.z); o.w = mul_f16x2(xu.w, xv.w);
+            if (idu[q] < 0) o = make_uint4(0u, 0u, 0u, 0u);
+            *cell = o;
+          }
         }
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive_on_cta(smem_u32(&bars.full[stage]), 0);
         if (t == 0) TR(10, c, group);
-      };
-      long long i = group;
-      Buf A, B;
-      if (i < total) issue(A, i);
-      while (i < total) {
-        if (i + NG < total) issue(B, i + NG);
-        consume(A, i);
-        i += NG;
-        if (i >= total) break;
-        if (i + NG < total) issue(A, i + NG);
-        consume(B, i);
-        i += NG;
       }
     } else {
       uint32_t ephase = 1u;
@@ -745,21 +826,22 @@ int tc3_ublock_nodes(int n, int row_bytes, long long M) {
   return (int)((n + nb - 1) / nb);
 }
 
-template <int H, bool HB, int NG, int EW>
+template <int H, bool HB, int NG, int NL>
 static int tc3_launch_g(const void *h, const int *pu, const int *pv, long long M, const MlpParams &prm, int L,
                         int apply_sigmoid, float *score, uint8_t *img, int n, int *tile_order, const TcScale *scale,
                         cudaStream_t stream) {
   const int nhidden = L - 1;
   const size_t fixed = (size_t)nhidden * (H / 2) * H * 2 +
                        (size_t)TC_BM * 32 + (size_t)nhidden * (H / 2) * 32 +          // bias K-step tiles
-                       sizeof(float) * (size_t)H + 2 * TC_BM * sizeof(int2) + sizeof(PipeBarriers);
+                       sizeof(float) * (size_t)H + 2 * TC_BM * sizeof(int2) + 2 * TC_BM * sizeof(int) +
+                       (HB ? (size_t)2 * P_VROWS * H * 2 : 0) + 32 + sizeof(PipeBarriers);
   const size_t budget = 227 * 1024;
   if (fixed + (size_t)(NG + 1) * P_STAGE_BYTES > budget) return EPS_ERR_UNSUPPORTED;   // the resident weights do not fit (H = 256, L >= 4)
   int ring = (int)std::min<size_t>((budget - fixed) / P_STAGE_BYTES, (size_t)P_MAX_RING);
   const char *rg = getenv("EPS_TC3_RING");    // cap the ring depth (A/B measurements)
   if (rg && atoi(rg) >= NG + 1) ring = std::min(ring, atoi(rg));
   const size_t smem = fixed + (size_t)ring * P_STAGE_BYTES;
-  auto kern = linkpred_tc3_kernel<H, HB, NG, EW>;
+  auto kern = linkpred_tc3_kernel<H, HB, NG, NL>;
   EPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long npair_tiles = (M + 2 * TC_BM - 1) / (2 * TC_BM);
   const int clusters = (int)std::min<long long>(npair_tiles, (long long)(sm_count() / 2));
@@ -771,7 +853,7 @@ static int tc3_launch_g(const void *h, const int *pu, const int *pv, long long M
     tile_order_kernel<<<1, TO_THREADS, 0, stream>>>(pu, M, npair_tiles, 2 * TC_BM, block_nodes, nblocks, tile_order);
     EPS_LAUNCH_CHECK();
   }
-  kern<<<2 * clusters, p_threads(NG, EW), smem, stream>>>(h, pu, pv, M, prm, L, apply_sigmoid, img, score, tune, ring,
+  kern<<<2 * clusters, p_threads(NG, NL), smem, stream>>>(h, pu, pv, M, prm, L, apply_sigmoid, img, score, tune, ring,
                                                      block_nodes > 0 ? tile_order : nullptr, scale);
   EPS_LAUNCH_CHECK();
 #ifdef EPS_TC3_TRACE
@@ -791,12 +873,20 @@ template <int H, bool HB>
 static int tc3_launch_h(const void *h, const int *pu, const int *pv, long long M, const MlpParams &prm, int L,
                         int apply_sigmoid, float *score, uint8_t *img, int n, int *tile_order, const TcScale *scale,
                         cudaStream_t stream) {
-  // producer groups: 2 (default: 14 warps -> 128 registers) or 3 (EPS_TC3_GROUPS=3: 18 warps -> 96 registers).
-  // A second epilogue warp per TMEM lane quarter was measured and dropped (profiles/round2_k2_epilogue_ab.md).
-  const char *g = getenv("EPS_TC3_GROUPS");
-  if (g && g[0] == '3')
-    return tc3_launch_g<H, HB, 3, 4>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, n, tile_order, scale, stream);
-  return tc3_launch_g<H, HB, 2, 4>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, n, tile_order, scale, stream);
+  // Warp budget (one CTA per SM): 4 epilogue + MMA + ids + NL loaders + 4 NG producers.
+  //   fp16 table: NL = 4 loaders + 1 group multiplying in place (14 warps -> 128 registers) by default;
+  //               EPS_TC3_SHAPE=42 / 81 / 82: NL NG = 4 2 / 8 1 / 8 2 (18-22 warps -> 96-80 registers) for A/B runs;
+  //   fp32 source (short lists): 2 groups that load through registers, no loaders.
+  if constexpr (HB) {
+    const char *e = getenv("EPS_TC3_SHAPE");
+    const int shape = e ? atoi(e) : 41;
+    if (shape == 42) return tc3_launch_g<H, true, 2, 4>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, n, tile_order, scale, stream);
+    if (shape == 81) return tc3_launch_g<H, true, 1, 8>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, n, tile_order, scale, stream);
+    if (shape == 82) return tc3_launch_g<H, true, 2, 8>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, n, tile_order, scale, stream);
+    return tc3_launch_g<H, true, 1, 4>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, n, tile_order, scale, stream);
+  } else {
+    return tc3_launch_g<H, false, 2, 0>(h, pu, pv, M, prm, L, apply_sigmoid, score, img, n, tile_order, scale, stream);
+  }
 }
 
 // ---- prepare kernels: scale, fp16 table, weight images (once per (h, weights); EPS_MLP_REUSE_WORKSPACE skips them) ----

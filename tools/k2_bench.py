@@ -16,7 +16,7 @@ def main():
     mlog = int(sys.argv[1]) if len(sys.argv) > 1 else 25
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
     dev = torch.device("cuda:0")
-    n, H, L, run = 576289, 256, 3, 14336
+    n, H, L, run = int(os.environ.get('K2_N', 576289)), 256, 3, 14336
     M = 1 << mlog
     g = torch.Generator(device=dev).manual_seed(0)
     h = torch.randn(n, H, device=dev, generator=g) * 0.5

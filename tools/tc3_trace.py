@@ -8,7 +8,7 @@
 import sys
 import numpy as np
 
-TAGS = {1: "mma acc_free ok", 2: "mma chunk full", 3: "mma a2 kb full", 4: "mma layer committed", 5: "epi acc_full ok",
+TAGS = {1: "mma acc_free ok", 2: "mma chunk full", 3: "mma a2 chunk full", 4: "mma layer committed", 5: "epi acc_full ok",
         6: "epi kb published", 7: "epi acc_free sent", 8: "prod loads issued", 9: "prod stage empty ok", 10: "prod stage published",
         11: "mma chunk MMAs issued", 12: "mma chunk committed", 13: "mma before full wait", 14: "mma after full wait"}
 
@@ -19,7 +19,8 @@ def run():
     n, H, L, M, runlen = 576289, 256, 3, 1 << 23, 14600
     g = torch.Generator().manual_seed(0)
     h = torch.randn(n, H, generator=g).cuda() * 0.3
-    u = torch.randint(0, n, (M,), generator=g, dtype=torch.int32)
+    owners = M // runlen + 1
+    u = torch.randint(0, n, (owners, runlen), generator=g, dtype=torch.int32).sort(dim=1)[0].reshape(-1)[:M].contiguous()
     v = (torch.arange(M) // runlen).to(torch.int32)
     e = torch.stack([u, v]).cuda()
     Ws = [torch.randn(H, H, generator=g).cuda() / 16 for _ in range(L - 1)] + [torch.randn(1, H, generator=g).cuda() / 16]
