@@ -8,20 +8,25 @@
 // in shared memory (with H = 256 one layer's fp16 weights are 128 KB: the pair splits the N dimension of the
 // B operand, 64 KB per SM and layer) and runs warp-specialised roles per CTA, connected by mbarriers:
 //
-//   producers (8 warps)  gather h[u], h[v] from an fp16 copy of h (128-bit loads, the next chunk's
-//                        loads in flight while the current one is converted), multiply (HMUL2)
-//                        and fill a ring of 128 x 32 K-chunks (K-major SWIZZLE_64B, 4 stages at H = 256);
+//   ids warp             (u, v) of a tile's 128 rows -> shared memory one tile ahead, plus the h[v] ROWS of the tile's
+//                        owners (the list is grouped by v: one owner per tile, now and then two) staged in shared memory;
+//   loaders (4 warps)    cp.async (LDGSTS) of the h[u] pieces of every 128 x 32 K-chunk straight into a ring of 8 KB
+//                        stages (K-major SWIZZLE_64B), completion counted on the stage's mbarrier: the whole ring
+//                        (9 stages at H = 256, L = 3) is in flight ahead of the tensor pipe and nobody waits for data;
+//   producers (4 warps)  multiply a landed chunk in place by h[v] (HMUL2, operands from shared memory only),
+//                        fence.proxy.async, hand the stage to the MMA issuer;
 //   MMA issuer (1 lane,  waits for a ring stage from BOTH CTAs, issues M=256 x N=H x K=16 UMMAs
-//   leader CTA only)     into one of two TMEM accumulator slots, releases stages / publishes
-//                        accumulators with multicast tcgen05.commit; later layers read their A operand
-//                        (the previous layer's activations) from a 3-slot ring of 64-column K-blocks;
-//   epilogue (4 warps)   thread-per-row: tcgen05.ld, + bias, ReLU, then either fp16 -> the activation
-//                        tile for the next layer — published per 64-column K-block, so the next
-//                        layer's MMAs start while the rest of the tile is still being converted —
-//                        or the fused H -> 1 output layer + sigmoid.
+//   leader CTA only)     into one of two TMEM accumulator slots, releases stages / publishes accumulators with
+//                        multicast tcgen05.commit; layers after the first read their A operand from TENSOR MEMORY;
+//   epilogue (4 warps)   thread-per-row: tcgen05.ld, ReLU, then either round to fp16 and tcgen05.st the packed chunk
+//                        back into the accumulator slot IN PLACE — it becomes the next layer's A operand, published
+//                        per 32-column chunk so the next layer's MMAs trail the conversion, and the activations never
+//                        touch shared memory — or the fused H -> 1 output layer + sigmoid.
 //
-// The two accumulator slots let the tensor pipe start the next GEMM (next layer, or next tile's first
-// layer) while the epilogue drains the previous one; the ring decouples the HBM/L2 gather from both.
+// The two accumulator slots let the tensor pipe start the next GEMM (next layer, or next tile's first layer) while
+// the epilogue drains the previous one; the ring decouples the HBM/L2 gather from both.  Short pair lists (no fp16
+// table) gather fp32 rows through registers instead (two producer groups, no loaders).
+// How the design got here, with the measurements behind every step: profiles/round2_d_k2_timeline.md.
 #include <cooperative_groups.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -341,17 +346,25 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
         tc_fence_after();
         if (tid == 0) TR(5, l, 0);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * H;
-        uint32_t buf[2][32];
-        tmem_ld32_issue(taddr, buf[0]);
+        // 16-column loads, the next one always in flight (same TMEM read rate as 32-column loads,
+        // tools/micro/tmem_ld_bw.cu, at half the registers: the kernel fits 96 registers without spills, which is what
+        // lets it run 18 warps)
+        constexpr int NLD = 2 * NCHUNK;
+        uint32_t buf[2][16];
+        tmem_ld16_issue(taddr, buf[0]);
         if (l < nhidden - 1) {
 #pragma unroll
           for (int c = 0; c < NCHUNK; ++c) {
-            tmem_ld_wait(buf[c & 1]);
-            if (c + 1 < NCHUNK) tmem_ld32_issue(taddr + (uint32_t)(c + 1) * 32u, buf[(c + 1) & 1]);
-            const uint32_t *v = buf[c & 1];
             uint32_t o[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = cvt_relu_f16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+            for (int hf = 0; hf < 2; ++hf) {
+              const int li = 2 * c + hf;
+              tmem_ld_wait16(buf[li & 1]);
+              if (li + 1 < NLD) tmem_ld16_issue(taddr + (uint32_t)(li + 1) * 16u, buf[(li + 1) & 1]);
+              const uint32_t *v = buf[li & 1];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[hf * 8 + j] = cvt_relu_f16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+            }
             tmem_st16(taddr + (uint32_t)c * 16u, o);
             tmem_st_wait();
             // the chunk is in place: the tensor pipe starts (continues) the next layer on it while the remaining
@@ -370,13 +383,13 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
           const float4 *w4 = reinterpret_cast<const float4 *>(sWlast);
           float2 part = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int c = 0; c < NCHUNK; ++c) {
-            tmem_ld_wait(buf[c & 1]);
-            if (c + 1 < NCHUNK) tmem_ld32_issue(taddr + (uint32_t)(c + 1) * 32u, buf[(c + 1) & 1]);
-            const uint32_t *v = buf[c & 1];
+          for (int li = 0; li < NLD; ++li) {
+            tmem_ld_wait16(buf[li & 1]);
+            if (li + 1 < NLD) tmem_ld16_issue(taddr + (uint32_t)(li + 1) * 16u, buf[(li + 1) & 1]);
+            const uint32_t *v = buf[li & 1];
 #pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-              const float4 wa = w4[(c * 32 + e) >> 2];
+            for (int e = 0; e < 16; e += 4) {
+              const float4 wa = w4[(li * 16 + e) >> 2];
               float2 t0 = make_float2(fmaxf(__uint_as_float(v[e + 0]), 0.f), fmaxf(__uint_as_float(v[e + 1]), 0.f));
               float2 t1 = make_float2(fmaxf(__uint_as_float(v[e + 2]), 0.f), fmaxf(__uint_as_float(v[e + 3]), 0.f));
               part = fma_f32x2(t0, make_float2(wa.x, wa.y), part);
@@ -845,8 +858,11 @@ static int tc3_launch_g(const void *h, const int *pu, const int *pv, long long M
   EPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long npair_tiles = (M + 2 * TC_BM - 1) / (2 * TC_BM);
   const int clusters = (int)std::min<long long>(npair_tiles, (long long)(sm_count() / 2));
-  const char *tn = getenv("EPS_TC3_TUNE");   // bit0: L2 row prefetch by the id warp (fp32-source path; default on)
-  const int tune = tn ? atoi(tn) : 1;
+  // EPS_TC3_TUNE bit 0: L2 prefetch of whole embedding rows by the ids warp, one tile ahead.  On for the fp32 source;
+  // off for the fp16 table, whose loaders run a tile ahead themselves (measured: 7.06 ms without, 7.20 with; a
+  // row-completing prefetch at the first chunk of a tile changed nothing either, gpurun_out/r3g_call.log)
+  const char *tn = getenv("EPS_TC3_TUNE");
+  const int tune = tn ? atoi(tn) : (HB ? 0 : 1);
   const int block_nodes = tile_order ? tc3_ublock_nodes(n, H * (HB ? 2 : 4), M) : 0;
   if (block_nodes > 0) {
     const int nblocks = (n + block_nodes - 1) / block_nodes;

@@ -124,7 +124,7 @@ class PrefilterToleranceError(RuntimeError):
 # roundings) the maximum over 2.6e5 draws sits near 4.6 sigma, so 2x is ~9 sigma — out of reach of 10^10 candidates.
 PREFILTER_TOL = 1e-2                   # ceiling: beyond this the arm is not a usable prefilter
 PREFILTER_SAFETY = 2.0
-PREFILTER_TOL_FLOOR = 2.5e-7          # ~4 ulp of a sigmoid output
+PREFILTER_TOL_FLOOR = 2e-5            # below this the sample statistic is the fp32 arm's own rounding noise (its error vs fp64 is ~1e-5)
 PREFILTER_CAL_SAMPLE = 1 << 17        # top-scoring + strided candidates of the first slab, each
 PREFILTER_POOL_CAP = 1 << 27          # pool entries beyond which the band is called too wide (-> fp32 arm)
 
