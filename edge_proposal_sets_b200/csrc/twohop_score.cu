@@ -40,15 +40,22 @@ constexpr int TS_DEFAULT_THREADS = 512;   // one-pass entry point (see eps_twoho
 constexpr int TS_LONG = 96;   // lists at least this long are streamed warp-wide without a search
 
 // Visit every element of the neighbour lists of N(v).  A warp takes LG lists at a time (LG = 32, 16, ... 1,
-// warp-uniform): the caller picks the largest LG that still gives every warp of the CTA a group, so an owner
-// of average degree (74 on the ppa shape) keeps all 16 warps busy instead of three — the kernel is
-// latency-bound, so idle warps are lost time.
+// warp-uniform), and the groups are HANDED OUT through a shared-memory counter: with a static round-robin an owner of
+// average degree (74 on the ppa shape) gave some warps two groups and the others one, and a warp that drew a hub's
+// list kept the other fifteen waiting — 46 % of all stall samples sat at the two barriers behind the walks
+// (ncu source counters, profiles/round2_e_twohop.md).  The caller picks the largest LG that still leaves ~4 groups
+// per warp to balance with.  `counter` is zero when the walk starts (the caller resets it behind a barrier).
 // f.visit(u, p) is called once per 2-path v - k - u (p = index of u in `col`, i.e. inside N(k)) after
 // f.select_slot*(lane that holds k's metadata).
 template <typename F>
 __device__ __forceinline__ void walk_two_paths(const int *__restrict__ rowptr, const int *__restrict__ col,
-                                               int vs, int ve, int warp, int nwarps, int lane, int LG, F f) {
-  for (int base = vs + warp * LG; base < ve; base += nwarps * LG) {
+                                               int vs, int ve, int lane, int LG, int *counter, F f) {
+  for (;;) {
+    int grp = 0;
+    if (lane == 0) grp = atomicAdd(counter, 1);
+    grp = __shfl_sync(FULL, grp, 0);
+    const int base = vs + grp * LG;
+    if (base >= ve) break;
     int k = -1, s = 0, len = 0;
     if (lane < LG && base + lane < ve) {
       k = __ldg(col + base + lane);
@@ -165,7 +172,8 @@ twohop_score_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
                     const float *__restrict__ wtable, int n, int v_lo, int v_hi,
                     const long long *__restrict__ offsets, int *__restrict__ pair_u,
                     int *__restrict__ pair_v, unsigned long long *__restrict__ acc, int *__restrict__ cn,
-                    unsigned int *owner_counter, unsigned int *__restrict__ counts_out) {
+                    unsigned int *owner_counter, unsigned int *__restrict__ counts_out,
+                    const int *__restrict__ owner_order, int n_order) {
   extern __shared__ uint32_t sm[];
   const int W = (n + 31) >> 5;       // bitmap words
   const int W2 = (W + 31) >> 5;      // blocks of 32 words
@@ -174,6 +182,7 @@ twohop_score_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
   uint32_t *blk = bm2 + W2;          // #candidates before block g
   uint16_t *pre = reinterpret_cast<uint16_t *>(blk + W2);   // #candidates before word w inside its block
   __shared__ int s_owner;
+  __shared__ int s_walk;             // next list group of the current walk
   __shared__ uint32_t s_scan[THREADS / 32];
   __shared__ uint32_t s_carry;
   const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
@@ -181,17 +190,24 @@ twohop_score_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
   for (int w = tid; w < W + W2; w += THREADS) sm[w] = 0;
   for (;;) {
     __syncthreads();
-    if (tid == 0) s_owner = v_lo + (int)atomicAdd(owner_counter, 1u);
+    if (tid == 0) {
+      // owners are handed out HEAVIEST FIRST when the caller supplies an order (one-pass entry point): a hub owner
+      // costs ~40 average owners, and drawn late by one CTA it kept the other 295 waiting — SMs were busy 48 % of the
+      // kernel's duration (profiles/round2_e_twohop.md)
+      const int t = (int)atomicAdd(owner_counter, 1u);
+      s_owner = (owner_order && t < n_order) ? v_lo + owner_order[t] : v_lo + t;
+      s_walk = 0;
+    }
     __syncthreads();
     const int v = s_owner;
     if (v >= v_hi) break;
     const int vs = __ldg(rowptr + v), ve = __ldg(rowptr + v + 1);
-    int LG = 32;                                           // lists per warp group: every warp gets a group
-    while (LG > 1 && (ve - vs + LG - 1) / LG < NW) LG >>= 1;
+    int LG = 32;                                           // lists per group: ~4 groups per warp to balance with
+    while (LG > 1 && (ve - vs + LG - 1) / LG < 4 * NW) LG >>= 1;
     const long long out_base = offsets[v - v_lo];
     if (offsets[v - v_lo + 1] == out_base) continue;   // no (room for) candidates (uniform): bitmap untouched
     // ---- 1. mark ----
-    walk_two_paths(rowptr, col, vs, ve, warp, NW, lane, LG, MarkVisitor{bm, bm2});
+    walk_two_paths(rowptr, col, vs, ve, lane, LG, &s_walk, MarkVisitor{bm, bm2});
     __syncthreads();
     // ---- 2. clear known edges and the diagonal ----
     for (int p = vs + tid; p < ve; p += THREADS) {
@@ -199,7 +215,7 @@ twohop_score_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
       atomicAnd(&bm[k >> 5], ~(1u << (k & 31)));
     }
     if (tid == 0) atomicAnd(&bm[v >> 5], ~(1u << (v & 31)));
-    if (tid == 0) s_carry = 0;
+    if (tid == 0) { s_carry = 0; s_walk = 0; }        // the first walk is over (barrier above): reset for the second
     __syncthreads();
     // ---- 3a. rank: thread t owns block c + t (32 bitmap words) ----
     for (int c = 0; c < W2; c += THREADS) {
@@ -278,7 +294,7 @@ twohop_score_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
       ScoreVisitor<HAS_W, WANT_CN, HAS_VAL> sv{bm, blk, pre, wtable, val,
                                                (HAS_W || HAS_VAL) ? acc + out_base : nullptr,
                                                WANT_CN ? cn + out_base : nullptr};
-      walk_two_paths(rowptr, col, vs, ve, warp, NW, lane, LG, sv);
+      walk_two_paths(rowptr, col, vs, ve, lane, LG, &s_walk, sv);
     }
     __syncthreads();
     // ---- 5. cleanup ----
@@ -305,6 +321,34 @@ twohop_finalize_kernel(const unsigned long long *__restrict__ acc, const int *__
     float sc = acc ? from_fixed(acc[i]) : (float)cn[i];
     if (flags & EPS_CN_SIGMOID) sc = sigmoidf_ref(sc);
     score[i] = sc;
+  }
+}
+
+// Owner order for the one-pass kernel, heaviest first: bucket b = 63 - floor(log2(slot size + 1)), so bucket 0 holds the
+// largest slots.  PASS 0 counts, PASS 1 turns the 64 counts into bases (one warp pair), PASS 2 scatters (order inside a
+// bucket is whatever the atomics give: the outputs do not depend on the order owners are processed in).
+template <int PASS>
+__global__ void __launch_bounds__(256)
+owner_bucket_kernel(const long long *__restrict__ boff, int n_own, unsigned int *__restrict__ buckets, int *__restrict__ order) {
+  if (PASS == 1) {
+    __shared__ unsigned int c[64];
+    const int t = threadIdx.x;
+    c[t] = buckets[t];
+    __syncthreads();
+    if (t == 0) {
+      unsigned int run = 0;
+      for (int b = 0; b < 64; ++b) { const unsigned int x = c[b]; c[b] = run; run += x; }
+    }
+    __syncthreads();
+    buckets[t] = c[t];
+    return;
+  }
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_own; i += stride) {
+    const unsigned long long sz = (unsigned long long)(boff[i + 1] - boff[i]) + 1ull;
+    const int b = __clzll((long long)sz);                 // 63 - floor(log2(sz)); sz >= 1
+    if (PASS == 0) atomicAdd(&buckets[b], 1u);
+    else order[atomicAdd(&buckets[b], 1u)] = i;
   }
 }
 
@@ -445,7 +489,7 @@ extern "C" int eps_twohop_scored(const int32_t *rowptr, const int32_t *col, cons
   }
   if (cn) EPS_CUDA(cudaMemsetAsync(cn, 0, (size_t)N * 4, stream));
   void (*kern)(const int *, const int *, const float *, const float *, int, int, int, const long long *, int *,
-               int *, unsigned long long *, int *, unsigned int *, unsigned int *);
+               int *, unsigned long long *, int *, unsigned int *, unsigned int *, const int *, int);
   if (wtable) kern = cn ? twohop_score_kernel<true, true, false> : twohop_score_kernel<true, false, false>;
   else kern = twohop_score_kernel<false, true, false>;
   EPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -455,7 +499,7 @@ extern "C" int eps_twohop_scored(const int32_t *rowptr, const int32_t *col, cons
   const int grid = (int)std::min<long long>((long long)(v_hi - v_lo), (long long)sms * occ);
   kern<<<grid, TS_THREADS, smem, stream>>>(rowptr, col, nullptr, wtable, n, v_lo, v_hi,
                                            (const long long *)offsets, pair_u, pair_v, acc, cn,
-                                           (unsigned int *)ws, nullptr);
+                                           (unsigned int *)ws, nullptr, nullptr, 0);
   EPS_LAUNCH_CHECK();
   if (score) {
     const int fgrid = (int)std::min<long long>((N + 255) / 256, (long long)sms * 8);
@@ -472,8 +516,8 @@ static inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 extern "C" size_t eps_twohop_onepass_workspace_bytes(int64_t cap, int32_t n_owners) {
   const size_t c = (size_t)(cap > 0 ? cap : 0), o = (size_t)(n_owners > 0 ? n_owners : 0);
-  // ticket | per-owner counts | padded u | padded CN counts | padded fixed-point sums
-  return 256 + up256(o * 4) + up256(c * 4) + up256(c * 4) + up256(c * 8);
+  // ticket | work buckets | per-owner counts | owner order | padded u | padded CN counts | padded fixed-point sums
+  return 512 + 2 * up256(o * 4) + up256(c * 4) + up256(c * 4) + up256(c * 8);
 }
 
 extern "C" int eps_twohop_onepass(const int32_t *rowptr, const int32_t *col, const float *val,
@@ -502,11 +546,13 @@ extern "C" int eps_twohop_onepass(const int32_t *rowptr, const int32_t *col, con
     return EPS_ERR_UNSUPPORTED;
   }
   uint8_t *ws = (uint8_t *)workspace;
-  unsigned int *counts = (unsigned int *)(ws + 256);
-  int *pad_u = (int *)(ws + 256 + up256((size_t)n_own * 4));
+  unsigned int *buckets = (unsigned int *)(ws + 256);
+  unsigned int *counts = (unsigned int *)(ws + 512);
+  int *order = (int *)(ws + 512 + up256((size_t)n_own * 4));
+  int *pad_u = (int *)(ws + 512 + 2 * up256((size_t)n_own * 4));
   int *pad_cn = (int *)((uint8_t *)pad_u + up256((size_t)cap * 4));
   unsigned long long *pad_acc = (unsigned long long *)((uint8_t *)pad_cn + up256((size_t)cap * 4));
-  EPS_CUDA(cudaMemsetAsync(ws, 0, 256 + up256((size_t)n_own * 4), stream));   // ticket + counts
+  EPS_CUDA(cudaMemsetAsync(ws, 0, 512 + up256((size_t)n_own * 4), stream));   // ticket + buckets + counts
   const bool want_score = score != nullptr || count != nullptr;
   unsigned long long *acc = nullptr;
   int *cn = nullptr;
@@ -519,7 +565,7 @@ extern "C" int eps_twohop_onepass(const int32_t *rowptr, const int32_t *col, con
   }
   if (cn) EPS_CUDA(cudaMemsetAsync(cn, 0, (size_t)cap * 4, stream));
   void (*kern)(const int *, const int *, const float *, const float *, int, int, int, const long long *, int *,
-               int *, unsigned long long *, int *, unsigned int *, unsigned int *);
+               int *, unsigned long long *, int *, unsigned int *, unsigned int *, const int *, int);
   // CTA size.  Measured (gpurun_out/r31, fused phase per step): 1024 threads help only where the bitmap limits
   // the kernel to 2 CTAs per SM (ppa 12.6 -> 11.6 ms) and hurt where 512-thread CTAs already fill the SM
   // (collab 4.6 -> 7.7 ms; ddi 8.1 -> 8.2): 512 stays the default, EPS_TS_THREADS=1024 overrides (A/B runs)
@@ -540,9 +586,16 @@ extern "C" int eps_twohop_onepass(const int32_t *rowptr, const int32_t *col, con
   EPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
   if (occ < 1) occ = 1;
   const int grid = (int)std::min<long long>((long long)n_own, (long long)sms * occ);
+  {  // heaviest-first hand-out: counting sort of the owners by the power of two of their slot size (the bound)
+    const int ogrid = std::min((n_own + 255) / 256, sms * 8);
+    owner_bucket_kernel<0><<<ogrid, 256, 0, stream>>>((const long long *)bound_offsets, n_own, buckets, order);
+    owner_bucket_kernel<1><<<1, 64, 0, stream>>>((const long long *)bound_offsets, n_own, buckets, order);
+    owner_bucket_kernel<2><<<ogrid, 256, 0, stream>>>((const long long *)bound_offsets, n_own, buckets, order);
+    EPS_LAUNCH_CHECK();
+  }
   kern<<<grid, threads, smem, stream>>>(rowptr, col, val, wtable, n, v_lo, v_hi,
                                            (const long long *)bound_offsets, pad_u, nullptr, acc, cn,
-                                           (unsigned int *)ws, counts);
+                                           (unsigned int *)ws, counts, order, n_own);
   EPS_LAUNCH_CHECK();
   owner_scan_kernel<<<1, 1024, 0, stream>>>(counts, n_own, (long long *)offsets_out);
   EPS_LAUNCH_CHECK();

@@ -1,0 +1,13 @@
+#!/bin/bash
+# GPU box: heuristic-kernel parity tests + a short bench (10 % of the owners) for the phase times
+TAG=${1:-r3j}
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_heuristics.py tests/test_gpu_shapes.py -m gpu -x -q 2>&1 | tail -3
+timeout 600 python bench.py --gpus 1 --steps 3 --warmup 3 --owners-frac 0.1 --no-cpu-baseline --no-extras > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.log
+python -c "
+import json; j=json.load(open('gpurun_out/${TAG}_bench.json'))
+print('value', j['value'], 'ms', j['ms_per_step'])
+print('phases', j['detail']['phase_ms_rank0'])
+print('roofline', {k: j['roofline'][k] for k in ('achieved','frac','ms_per_launch','launches_per_step')})
+for r in j['roofline_other']: print('  other', {k: r[k] for k in ('kernel','achieved','frac','ms_per_launch','launches_per_step')})
+"
