@@ -211,7 +211,7 @@ def test_fused_twohop_scored_vs_oracle(shape):
 
 @pytest.mark.parametrize("shape", ["tiny", "small", "twitch"])
 def test_onepass_equals_twopass(shape):
-    """eps_twohop_onepass (decoupled look-back, outputs sized by a bound) == count pass + prefix sum +
+    """eps_twohop_onepass (padded per-owner slots sized by a bound, then scan + compaction) == count pass + prefix sum +
     fill / fused kernels, bit for bit: pairs, order, scores, counts, per-owner offsets."""
     from edge_proposal_sets_b200 import candidates
     from edge_proposal_sets_b200._lib import EpsError
