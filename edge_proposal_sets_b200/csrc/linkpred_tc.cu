@@ -691,7 +691,10 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
         if (pstage >= (uint32_t)ring) { pstage -= (uint32_t)ring; lphase ^= 1u; }
         if (t == 0) TR(9, c, group);
         uint8_t *dst = sRing + stage * P_STAGE_BYTES;
-        if (uni) {
+        if (tune & 32) {
+          // EXPERIMENT (EPS_TC3_TUNE bit 5, wrong scores): no multiply pass — what the kernel would run at if the A operand
+          // needed no shared-memory read-modify-write
+        } else if (uni) {
           // the thread's four rows share one staged owner row (almost always): all five shared-memory loads are issued
           // before the first multiply, so the chunk costs ONE load latency, not four in a row
           const uint4 xv = *reinterpret_cast<const uint4 *>(sVt + kq[0] * (H * 2) + boff);       // warp-wide broadcast
