@@ -6,12 +6,15 @@
 // arithmetic (fp32 products, fp32 accumulate, k ascending) and is the precision baseline the
 // tcgen05 arm (linkpred_tc.cu) is measured against; it is bounded by the fp32 FFMA rate, not by
 // HBM.  One CTA owns a tile of 32 pairs; activations ping-pong between two shared-memory
-// buffers, weights stream through L1/L2 (256 KB per layer, L2-resident).
+// buffers, weights stream through L1/L2 (256 KB per layer, L2-resident).  A thread computes TWO output
+// features for all 32 rows: every broadcast LDS.128 of an activation piece then feeds 8 FFMAs instead of 4 —
+// with one feature per thread the shared-memory pipe (32 wavefronts per 128 FFMA) was as busy as the FFMA pipe.
+// Each (row, feature) sum is still ONE fmaf chain in ascending k: the scores are bit-identical to round 1.
 #include "eps_common.cuh"
 
 namespace eps {
 
-constexpr int MLP_THREADS = 256;
+constexpr int MLP_THREADS = 128;
 constexpr int MLP_BM = 32;
 
 __global__ void __launch_bounds__(MLP_THREADS)
@@ -49,25 +52,35 @@ linkpred_fp32_kernel(const float *__restrict__ h, int H, const int *__restrict__
     for (int l = 0; l < L - 1; ++l) {
       const float *W = Wd[l];
       const float *b = bd[l];
-      for (int j = tid; j < H; j += MLP_THREADS) {
-        float acc[MLP_BM];
+      for (int j = tid; j < H; j += 2 * MLP_THREADS) {
+        const int j1 = j + MLP_THREADS;                       // second feature of this thread (if it exists)
+        const bool two = j1 < H;
+        float acc0[MLP_BM], acc1[MLP_BM];
 #pragma unroll
-        for (int r = 0; r < MLP_BM; ++r) acc[r] = 0.f;
-        const float4 *wrow = reinterpret_cast<const float4 *>(W + (size_t)j * H);
+        for (int r = 0; r < MLP_BM; ++r) { acc0[r] = 0.f; acc1[r] = 0.f; }
+        const float4 *wrow0 = reinterpret_cast<const float4 *>(W + (size_t)j * H);
+        const float4 *wrow1 = reinterpret_cast<const float4 *>(W + (size_t)(two ? j1 : j) * H);
         for (int k4 = 0; k4 < H4; ++k4) {
-          const float4 w = __ldg(wrow + k4);
+          const float4 w0 = __ldg(wrow0 + k4), w1 = __ldg(wrow1 + k4);
 #pragma unroll
           for (int r = 0; r < MLP_BM; ++r) {
             const float4 a = *reinterpret_cast<const float4 *>(zin + r * H + k4 * 4);
-            acc[r] = fmaf(a.x, w.x, acc[r]);
-            acc[r] = fmaf(a.y, w.y, acc[r]);
-            acc[r] = fmaf(a.z, w.z, acc[r]);
-            acc[r] = fmaf(a.w, w.w, acc[r]);
+            acc0[r] = fmaf(a.x, w0.x, acc0[r]);
+            acc0[r] = fmaf(a.y, w0.y, acc0[r]);
+            acc0[r] = fmaf(a.z, w0.z, acc0[r]);
+            acc0[r] = fmaf(a.w, w0.w, acc0[r]);
+            acc1[r] = fmaf(a.x, w1.x, acc1[r]);
+            acc1[r] = fmaf(a.y, w1.y, acc1[r]);
+            acc1[r] = fmaf(a.z, w1.z, acc1[r]);
+            acc1[r] = fmaf(a.w, w1.w, acc1[r]);
           }
         }
-        const float bj = __ldg(b + j);
+        const float b0 = __ldg(b + j), b1 = __ldg(b + (two ? j1 : j));
 #pragma unroll
-        for (int r = 0; r < MLP_BM; ++r) zout[r * H + j] = fmaxf(__fadd_rn(acc[r], bj), 0.f);
+        for (int r = 0; r < MLP_BM; ++r) {
+          zout[r * H + j] = fmaxf(__fadd_rn(acc0[r], b0), 0.f);
+          if (two) zout[r * H + j1] = fmaxf(__fadd_rn(acc1[r], b1), 0.f);
+        }
       }
       __syncthreads();
       float *t = zin; zin = zout; zout = t;

@@ -161,3 +161,40 @@ def test_tc_context_reuses_table_and_weight_images():
         assert torch.equal(ctx.score(part), ops.linkpred_mlp(hd, part, Ws, bs, "f16"))
     assert ctx.prepared
     assert torch.equal(ctx.score(ed, sigmoid=False), ops.linkpred_mlp(hd, ed, Ws, bs, "f16", sigmoid=False))
+
+
+@pytest.mark.timeout(180)
+def test_tc_arm_scores_do_not_depend_on_warp_shape_or_list_structure():
+    """The tensor-core arm's score is a function of (h, weights, u, v) only: the loader / producer warp shapes of the
+    A/B knob (EPS_TC3_SHAPE), the ring depth, and where a pair sits in the list (inside a long owner run, at a run
+    boundary, in a tile with more owners than the staged-row cache holds) must give the same bits."""
+    import os
+    from edge_proposal_sets_b200 import ops
+    H, L, n = 256, 3, 6000
+    sd, h, _, Ws, bs = _setup(H, L, n, 8, seed=11)
+    hd = torch.from_numpy(h).to(DEV)
+    rng = np.random.default_rng(5)
+    # owner runs of very different lengths: 1 .. 700 pairs, ascending u inside a run (what K6 emits), then a random tail
+    lens = rng.integers(1, 700, size=120)
+    v = np.repeat(rng.permutation(n)[:120], lens)
+    u = np.concatenate([np.sort(rng.integers(0, n, size=l)) for l in lens])
+    tail = rng.integers(0, n, size=(2, 3000))
+    e = np.concatenate([np.stack([u, v]), tail], axis=1)
+    ed = torch.from_numpy(e).to(DEV)
+    assert e.shape[1] >= 2 * n                                  # the fp16-table path
+    base = ops.linkpred_mlp(hd, ed, Ws, bs, "f16")
+    ref = ops.linkpred_mlp(hd, ed, Ws, bs, "fp32")
+    assert float((base - ref).abs().max()) <= 3e-4
+    try:
+        for key, val in (("EPS_TC3_SHAPE", "42"), ("EPS_TC3_SHAPE", "81"), ("EPS_TC3_SHAPE", "82"), ("EPS_TC3_RING", "3")):
+            os.environ[key] = val
+            got = ops.linkpred_mlp(hd, ed, Ws, bs, "f16")
+            os.environ.pop(key)
+            assert torch.equal(got, base), f"{key}={val} changed the scores"
+    finally:
+        os.environ.pop("EPS_TC3_SHAPE", None)
+        os.environ.pop("EPS_TC3_RING", None)
+    # the same pairs in a different order (shuffled: every tile has many owners) score the same
+    perm = torch.randperm(ed.shape[1], device=DEV)
+    got = ops.linkpred_mlp(hd, ed[:, perm].contiguous(), Ws, bs, "f16")
+    assert torch.equal(got, base[perm])
