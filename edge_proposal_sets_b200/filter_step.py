@@ -109,6 +109,18 @@ def iter_slabs(adj: SparseAdj, v_lo: int, v_hi: int, slab_pairs: int) -> Iterato
         lo = hi
 
 
+def owner_cost(adj: SparseAdj, jobs) -> torch.Tensor:
+    """Per-owner cost estimate that the multi-GPU owner ranges are balanced on.  Enumeration (K6) costs the owner's
+    2-paths; scoring a candidate with a GNN filter model (K2) costs ~8 x a 2-path visit (measured on the ppa shape:
+    0.218 ns per candidate against 0.029 ns per 2-path), and the candidate count is bounded by the owner's slot size
+    (candidates.owner_bounds).  Balancing on 2-paths alone left the ranks with few hubs 5 % more candidates and the
+    others waiting at the merge (N = 4: 33 ms of a 615 ms step)."""
+    work = candidates.two_path_work(adj).double()
+    if any((j.name if hasattr(j, "name") else j[0]) in GNN_MODELS for j in jobs):
+        work = work + 8.0 * candidates.owner_bounds(adj).double()
+    return work
+
+
 class PrefilterToleranceError(RuntimeError):
     """The fp16 tensor-core scores left their stated tolerance band around the fp32 scores; the
     caller re-runs on the fp32 arm (``filter_topk`` does)."""
@@ -333,7 +345,7 @@ def _filter_multi(jobs, x, adj: SparseAdj, k: Optional[int] = None, slab_pairs: 
     o_lo, o_hi = (0, adj.n) if owners is None else (max(int(owners[0]), 0), min(int(owners[1]), adj.n))
     v_lo, v_hi = o_lo, o_hi
     if world > 1:
-        bounds = parallel.partition_by_work(candidates.two_path_work(adj)[o_lo:o_hi], world)
+        bounds = parallel.partition_by_work(owner_cost(adj, jobs)[o_lo:o_hi], world)
         v_lo, v_hi = o_lo + bounds[rank], o_lo + bounds[rank + 1]
     # per job: scoring plan + running proposal set
     plans = []
