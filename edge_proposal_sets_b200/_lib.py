@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libeps_b200.so")
 
 EPS_OK = 0
-EPS_VERSION = 200          # must equal EPS_VERSION in include/eps.h (checked by load())
+EPS_VERSION = 201          # must equal EPS_VERSION in include/eps.h (checked by load())
 EPS_REDUCE_SUM, EPS_REDUCE_MEAN = 0, 1
 EPS_CN_SIGMOID, EPS_CN_GROUPED_BY_V = 1, 2
 EPS_MLP_FP32, EPS_MLP_TC_F16 = 0, 1
@@ -36,6 +36,8 @@ SIGNATURES = {
     "eps_linkpred_mlp": (_int, [_vp, _i32, _i32, _vp, _vp, _i64, C.POINTER(_vp), C.POINTER(_vp), _i32,
                                 _int, _int, _vp, _vp, _sz, _vp]),
     "eps_linkpred_workspace_bytes": (_sz, [_i32, _i32, _i32, _i64, _int]),
+    "eps_pair_hadamard_f32": (_int, [_vp, _i32, _i32, _vp, _vp, _i64, _vp, _vp]),
+    "eps_pair_hadamard_bwd_f32": (_int, [_vp, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _vp]),
     "eps_topk_f32": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     "eps_topk_workspace_bytes": (_sz, [_i64, _i64]),
     "eps_pack_edges": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),

@@ -12,8 +12,10 @@ to be transposed:
   * weighted GCN norm    val_ij = (w·dinv_i)·dinv_j — permuted once per graph (``transposed_values``);
   * SAGE mean            A = D⁻¹·S with S the 0/1 structure  =>  Aᵀ·dy = S·(D⁻¹ dy): the rows of dy
                          are scaled by 1/deg and summed with the structure-only kernel.
-The dense parts of a training step (x·W, the LinkPredictor layers, Adam) stay in torch / cuBLAS:
-they are plain library GEMMs, not the hot path of this repository.
+The LinkPredictor's input z0 = h[u] * h[v] and its backward (scatter-add into dh) are K7
+(``eps_pair_hadamard_f32`` / ``_bwd_f32``): one fused pass each instead of two index_select + mul and
+their three autograd backward launches.  The dense layers of a training step (x·W, the
+LinkPredictor's Linear layers, Adam) stay in torch / cuBLAS: plain library GEMMs.
 """
 from __future__ import annotations
 
@@ -61,3 +63,22 @@ def spmm(x: torch.Tensor, rowptr: torch.Tensor, col: torch.Tensor, val: Optional
     (``None``: the matrix is numerically symmetric); ``inv_deg`` = 1/row-length for ``reduce="mean"``
     (0 for empty rows)."""
     return _SpMM.apply(x, rowptr, col, val, val if val_t is None else val_t, reduce, inv_deg)
+
+
+class _PairHadamard(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, edges):
+        h = h.contiguous()
+        ctx.save_for_backward(h)
+        ctx.edges = edges
+        return ops.pair_hadamard(h, edges)
+
+    @staticmethod
+    def backward(ctx, gz):
+        (h,) = ctx.saved_tensors
+        return ops.pair_hadamard_bwd(h, ctx.edges, gz), None
+
+
+def pair_hadamard(h: torch.Tensor, edges: torch.Tensor) -> torch.Tensor:
+    """Differentiable (w.r.t. ``h``) K7: h[edges[0]] * h[edges[1]] -> [B,H]."""
+    return _PairHadamard.apply(h, edges)

@@ -186,6 +186,15 @@ class LinkPredictor(nn.Module):
         images built once): ``ctx.score(edges)`` == ``score_pairs(h, edges, "f16")``."""
         return ops.LinkpredTC(h, [l.weight for l in self.lins], [l.bias for l in self.lins])
 
+    def forward_pairs(self, h: torch.Tensor, edges: torch.Tensor) -> torch.Tensor:
+        """Training-mode forward from the embedding table (models.py:478-485 after models.py:506): z0 by K7
+        (``autograd.pair_hadamard``: one fused gather-multiply, scatter-add backward), then the Linear layers."""
+        from . import autograd
+        x = autograd.pair_hadamard(h, edges)
+        for lin in self.lins[:-1]:
+            x = F.dropout(F.relu(lin(x)), p=self.dropout, training=self.training)
+        return torch.sigmoid(self.lins[-1](x))
+
     def forward(self, x_i, x_j):
         """Reference signature (two gathered [B,H] blocks) kept for callers that use it."""
         if torch.is_grad_enabled() and (self.training or x_i.requires_grad or x_j.requires_grad):
@@ -242,8 +251,7 @@ class LinkGNN(nn.Module):
         if self.training and torch.is_grad_enabled():
             # train_and_eval.py:60: the whole GNN runs per batch, with autograd (models.py:500-506)
             h = self.gnn(self._input(x), adj)
-            e = edges.long()
-            return self.linkpred(h[e[0]], h[e[1]])
+            return self.linkpred.forward_pairs(h, edges)
         with torch.no_grad():
             h = self.embed(x, adj)
             return self.linkpred.score_pairs(h, edges).unsqueeze(1)   # [B,1] like the reference

@@ -83,6 +83,35 @@ def spmm_csr(rowptr: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor
     return y
 
 
+def pair_hadamard(h: torch.Tensor, edges: torch.Tensor) -> torch.Tensor:
+    """K7 forward: z0[b,:] = h[u_b,:] * h[v_b,:] for edges [2,B] -> fp32 [B,H] (training-mode input of the MLP)."""
+    _need_cuda(h, edges)
+    lib = _lib.load()
+    h = h.contiguous().float()
+    pu, pv = _pairs(edges)
+    M = pu.numel()
+    out = torch.empty((M, h.shape[1]), dtype=torch.float32, device=h.device)
+    check(lib.eps_pair_hadamard_f32(_ptr(h), h.shape[0], h.shape[1], _ptr(pu), _ptr(pv), M, _ptr(out), _stream()),
+          "eps_pair_hadamard_f32")
+    LAUNCHES["n"] += 1
+    return out
+
+
+def pair_hadamard_bwd(h: torch.Tensor, edges: torch.Tensor, dz: torch.Tensor) -> torch.Tensor:
+    """K7 backward: dh[u_b] += dz[b] * h[v_b], dh[v_b] += dz[b] * h[u_b] -> fp32 [n,H]."""
+    _need_cuda(h, edges, dz)
+    lib = _lib.load()
+    h = h.contiguous().float()
+    dz = dz.contiguous().float()
+    pu, pv = _pairs(edges)
+    M = pu.numel()
+    dh = torch.zeros_like(h)
+    check(lib.eps_pair_hadamard_bwd_f32(_ptr(h), h.shape[0], h.shape[1], _ptr(pu), _ptr(pv), M, _ptr(dz), _ptr(dh),
+                                        _stream()), "eps_pair_hadamard_bwd_f32")
+    LAUNCHES["n"] += 1
+    return dh
+
+
 def cn_aa(adj: SparseAdj, edges: torch.Tensor, wtable: Optional[torch.Tensor] = None,
           use_values: bool = True, sigmoid: bool = False, grouped_by_v: bool = False,
           want_count: bool = False):

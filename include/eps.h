@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define EPS_VERSION 200 /* 0.2.0; edge_proposal_sets_b200/_lib.py checks it at load time */
+#define EPS_VERSION 201 /* 0.2.1; edge_proposal_sets_b200/_lib.py checks it at load time */
 
 typedef enum {
   EPS_OK = 0,
@@ -140,6 +140,21 @@ int eps_linkpred_mlp(const float *h, int32_t n, int32_t H, const int32_t *pair_u
                      const float *const *b_h, int32_t L, int precision, int apply_sigmoid,
                      float *score, void *workspace, size_t workspace_bytes, void *stream);
 size_t eps_linkpred_workspace_bytes(int32_t n, int32_t H, int32_t L, int64_t M, int precision);
+
+/* ---------------------------------------------------------------------------
+ * K7  pair Hadamard gather (training mode of the LinkPredictor) and its backward
+ * replaces: h[edges[0]], h[edges[1]] (/root/reference/models.py:506) and x_i * x_j
+ *           (/root/reference/models.py:479) inside the training forward
+ *           (/root/reference/train_and_eval.py:60-66), and their autograd backward.
+ *   forward : out[b,:] = h[pair_u[b],:] * h[pair_v[b],:]              out fp32 [M,H]
+ *   backward: dh[pair_u[b],:] += dz[b,:] * h[pair_v[b],:]
+ *             dh[pair_v[b],:] += dz[b,:] * h[pair_u[b],:]              dh fp32 [n,H], caller-zeroed, fp32 atomics
+ * H must be a multiple of 4.
+ * ------------------------------------------------------------------------- */
+int eps_pair_hadamard_f32(const float *h, int32_t n, int32_t H, const int32_t *pair_u, const int32_t *pair_v,
+                          int64_t M, float *out, void *stream);
+int eps_pair_hadamard_bwd_f32(const float *h, int32_t n, int32_t H, const int32_t *pair_u, const int32_t *pair_v,
+                              int64_t M, const float *dz, float *dh, void *stream);
 
 /* ---------------------------------------------------------------------------
  * K4  top-k proposal selection

@@ -136,3 +136,26 @@ def test_submit_job_flow_train_filter_rank(tmp_path):
             "--sorted_edge_path", out.name, "--num_sorted_edge", "2000")
     assert r.returncode == 0, r.stderr[-3000:]
     assert "Using 2000 highest scoring edges" in r.stdout and r.stdout.count("Hits@20") >= 1
+
+
+@pytest.mark.timeout(120)
+def test_pair_hadamard_kernel_forward_bit_exact_backward_vs_autograd():
+    """K7 (eps_pair_hadamard_f32 / _bwd_f32), the LinkPredictor's training-mode input: the forward equals
+    h[u] * h[v] bit for bit, the backward equals autograd's scatter of the index_select / mul graph up to
+    fp32 summation order (repeated nodes: many pairs add into one row)."""
+    from edge_proposal_sets_b200 import autograd as ag
+    torch.manual_seed(0)
+    n, H, B = 500, 256, 20000
+    h = torch.randn(n, H, device=DEV, requires_grad=True)
+    e = torch.randint(0, n, (2, B), device=DEV)
+    e[:, :50] = 7                                              # self pairs and a hot node
+    z = ag.pair_hadamard(h, e)
+    zr = h[e[0]] * h[e[1]]
+    assert torch.equal(z, zr)
+    g = torch.randn(B, H, device=DEV)
+    (dh,) = torch.autograd.grad(z, h, g)
+    h64 = h.detach().double().requires_grad_(True)
+    (dr,) = torch.autograd.grad(h64[e[0]] * h64[e[1]], h64, g.double())
+    assert float((dh.double() - dr).abs().max()) <= 1e-5 * float(dr.abs().max())
+    # empty batch
+    assert ag.pair_hadamard(h, e[:, :0]).shape == (0, H)
