@@ -38,6 +38,7 @@ namespace eps {
 constexpr int TS_THREADS = 512;           // two-pass entry point
 constexpr int TS_DEFAULT_THREADS = 512;   // one-pass entry point (see eps_twohop_onepass)
 constexpr int TS_LONG = 96;   // lists at least this long are streamed warp-wide without a search
+constexpr int TS_DEPTH = 8;   // ... with this many loads in flight per lane (a hub owner's walk is one CTA's latency chain)
 
 // Visit every element of the neighbour lists of N(v).  A warp takes LG lists at a time (LG = 32, 16, ... 1,
 // warp-uniform), and the groups are HANDED OUT through a shared-memory counter: with a static round-robin an owner of
@@ -63,7 +64,7 @@ __device__ __forceinline__ void walk_two_paths(const int *__restrict__ rowptr, c
       len = __ldg(rowptr + k + 1) - s;
     }
     f.load_slot(k, base + lane);
-    // ---- long lists: the whole warp streams one list, 4 loads in flight per lane ----
+    // ---- long lists: the whole warp streams one list, TS_DEPTH loads in flight per lane ----
     unsigned longmask = __ballot_sync(FULL, len >= TS_LONG);
     while (longmask) {
       const int b = __ffs(longmask) - 1;
@@ -72,15 +73,15 @@ __device__ __forceinline__ void walk_two_paths(const int *__restrict__ rowptr, c
       const int lb = __shfl_sync(FULL, len, b);
       f.select_slot(b);
       const int *__restrict__ lp = col + sb;
-      for (int off = 0; off < lb; off += 128) {
-        int u[4];
+      for (int off = 0; off < lb; off += 32 * TS_DEPTH) {
+        int u[TS_DEPTH];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < TS_DEPTH; ++q) {
           const int p = off + q * 32 + lane;
           u[q] = p < lb ? __ldg(lp + p) : -1;
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+        for (int q = 0; q < TS_DEPTH; ++q)
           if (u[q] >= 0) f.visit(u[q], sb + off + q * 32 + lane);
       }
     }
