@@ -201,6 +201,7 @@ struct PipeBarriers {
   uint64_t a2_full[P_MAX_CHUNKS];  // epilogue (both CTAs) -> MMA issuer: 32-column chunk c of the activations is in TMEM
   uint64_t ids_full[2];        // ids warp -> producers                      (CTA-local)
   uint64_t ids_empty[2];       // producers -> ids warp                      (CTA-local)
+  uint64_t wload;              // TMA bulk copies of the resident weights -> everyone (once per kernel)
   uint32_t tmem_base_slot;
 };
 
@@ -278,12 +279,18 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
       mbar_init(smem_u32(&bars.ids_full[i]), 1);
       mbar_init(smem_u32(&bars.ids_empty[i]), P_PROD_WARPS + NL);
     }
+    mbar_init(smem_u32(&bars.wload), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (int l = 0; l < nhidden; ++l) {
-    const uint4 *src = reinterpret_cast<const uint4 *>(wimg + (size_t)l * H * H * 2 + (size_t)cta_rank * WH_BYTES);
-    uint4 *dst = reinterpret_cast<uint4 *>(sW + (size_t)l * WH_BYTES);
-    for (int i = tid; i < WH_BYTES / 16; i += P_THREADS) dst[i] = __ldg(src + i);
+    // The resident weights: this CTA's half of every hidden layer's pre-swizzled image (64 KB per layer at H = 256) comes
+    // in with one TMA bulk copy per layer (cp.async.bulk, SASS UBLKCP) straight from the async proxy the MMA reads
+    // with — no registers, no generic-proxy stores to fence; everybody waits for the byte count below.
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"(smem_u32(&bars.wload)), "r"((uint32_t)(nhidden * WH_BYTES)) : "memory");
+    for (int l = 0; l < nhidden; ++l)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   :: "r"(smem_u32(sW + (size_t)l * WH_BYTES)),
+                      "l"(wimg + (size_t)l * H * H * 2 + (size_t)cta_rank * WH_BYTES), "r"((uint32_t)WH_BYTES),
+                      "r"(smem_u32(&bars.wload)) : "memory");
   }
   // Biases ride in the MMA: one extra K = 16 step per hidden layer with A = [1 1 1 0 ...] for every
   // row and B[n] = [hi mid lo 0 ...], S times the bias of output feature n split into three fp16 terms
@@ -309,6 +316,8 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
   for (int i = tid; i < H; i += P_THREADS) sWlast[i] = __ldg(prm.W[L - 1] + i) * invS;   // exact: S is a power of two
   const float b_last = __ldg(prm.b[L - 1]);
   fence_async_smem();
+  __syncthreads();                                            // the barrier objects are initialised
+  mbar_wait_cluster(smem_u32(&bars.wload), 0u);               // the weights have landed
   tc_fence_before();
   cluster.sync();
   tc_fence_after();
