@@ -6,7 +6,6 @@
 
 namespace eps {
 
-constexpr int TC_THREADS = 256;
 constexpr int TC_BM = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -36,17 +35,6 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void mbar_init(uint32_t saddr, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(saddr), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t saddr, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t}\n"
-      :: "r"(saddr), "r"(parity) : "memory");
-}
-
 // ---- operand format of the tensor-core arm: IEEE fp16 (11-bit significand), fp32 accumulate ----
 // fp16 runs at the same tcgen05 rate as bf16 and carries three more significand bits: measured on the ppa-shape
 // filter model the score deviation from the fp32 arm drops 8x, which is what lets the tensor-core scores serve
