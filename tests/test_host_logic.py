@@ -165,3 +165,23 @@ def test_values_symmetric_detects_asymmetric_weights():
     g.val = g.val.copy()
     g.val[0] += 1.0
     assert not candidates.values_symmetric(to_adj(g, "cpu", keep_values=True))
+
+
+def test_owner_cost_balances_scoring_and_enumeration():
+    """filter_step.owner_cost: 2-paths for the heuristic jobs, 2-paths + 8 x slot size as soon as a GNN model scores;
+    the ranges cut on it are contiguous, cover every owner and carry near-equal cost."""
+    import torch
+    from edge_proposal_sets_b200 import candidates, filter_step, parallel
+    from util import synth_graph, to_adj
+    s, ei, w, g = synth_graph("small")
+    adj = to_adj(g, "cpu")
+    two = candidates.two_path_work(adj).double()
+    heur = filter_step.owner_cost(adj, [filter_step.FilterJob("adamic_ogb", None)])
+    assert torch.equal(heur, two)
+    gnn = filter_step.owner_cost(adj, [filter_step.FilterJob("adamic_ogb", None), ("gcn", None)])
+    assert torch.equal(gnn, two + 8.0 * candidates.owner_bounds(adj).double())
+    for parts in (2, 3, 8):
+        b = parallel.partition_by_work(gnn, parts)
+        assert b[0] == 0 and b[-1] == adj.n and all(b[i] <= b[i + 1] for i in range(parts))
+        loads = [float(gnn[b[i]:b[i + 1]].sum()) for i in range(parts)]
+        assert max(loads) <= float(gnn.sum()) / parts + float(gnn.max()) + 1e-9
