@@ -318,6 +318,12 @@ class Workload:
         ew = host["edge_weight"] if host["edge_weight"] is not None else torch.ones(host["edge_index"].shape[1])
         adj0 = pg.add_edges(host["dataset"], host["edge_index"].to(dev), ew.to(dev),
                             torch.zeros([2, 0], dtype=torch.long, device=dev), n)
+        # rows of the node features / embedding table this rank's share of the row-sharded GNN reads (a function of
+        # the graph alone: models._ConvStack.embed_rows cuts the same ranges)
+        self.rank = int(os.environ.get("RANK", "0")) if world > 1 else 0
+        from edge_proposal_sets_b200 import parallel as _par
+        rb = _par.row_partition(adj0.gcn_norm()[0], n, world)
+        self.rows = (rb[self.rank], rb[self.rank + 1])
         self.h_rowptr, self.h_col = pinf(adj0.rowptr.cpu()), pinf(adj0.col.cpu())
         self.h_val = None if adj0.val is None else pinf(adj0.val.cpu())
         self.h_x = None if host["x"] is None else pinf(host["x"])
@@ -340,6 +346,11 @@ class Workload:
                              ([self.h_val] if self.h_val is not None else []) +
                              ([self.h_x] if self.h_x is not None else []) + list(self.h_sd.values()))
         self.owners = None if args.owners_frac >= 1.0 else (0, max(1, int(n * args.owners_frac)))
+        # end-to-end upload at N > 1: the whole graph, but only this rank's ROW SHARD of the node-indexed inputs
+        frac = (self.rows[1] - self.rows[0]) / max(n, 1)
+        node_indexed = ([self.h_x] if self.h_x is not None else []) + [v for k_, v in self.h_sd.items() if k_ == "emb.weight"]
+        full_nodes = sum(t.numel() * t.element_size() for t in node_indexed)
+        self.h2d_bytes_sharded = int(self.h2d_bytes - full_nodes + full_nodes * frac) if world > 1 else self.h2d_bytes
 
     def calibrate_model(self):
         """Rescale the output layer so that the fp32 logits of ~10^6 candidates have mean -2, std 2 (see
@@ -362,18 +373,32 @@ class Workload:
         self.model_scale = dict(sample=int(edges.shape[1]), logit_mean_before=mean, logit_std_before=std, scale=scale)
         self.model._h_key = None
 
-    def upload(self):
-        """H2D of everything the public call takes (graph first; features + weights on a copy stream)."""
+    def upload(self, shard: bool = False):
+        """H2D of everything the public call takes (graph first; features + weights on a copy stream).
+        ``shard`` (the end-to-end loop at N > 1): of the node-indexed inputs — features and the embedding table —
+        only the rows this rank's share of the row-sharded GNN reads (``self.rows``) are copied; the other rows of
+        the device buffers are never read by this rank (embed_rows slices before it computes)."""
         import torch
         from edge_proposal_sets_b200 import graph as pg
         dev = self.dev
         adj = pg.SparseAdj(self.h_rowptr.to(dev, non_blocking=True), self.h_col.to(dev, non_blocking=True),
                            None if self.h_val is None else self.h_val.to(dev, non_blocking=True), self.n)
+        part = shard and self.world > 1
+        lo, hi = self.rows
         self.copy_stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.copy_stream), torch.no_grad():
-            x = None if self.h_x is None else self.h_x.to(dev, non_blocking=True)
+            x = None
+            if self.h_x is not None:
+                if part:
+                    x = torch.empty(self.h_x.shape, dtype=self.h_x.dtype, device=dev)
+                    x[lo:hi].copy_(self.h_x[lo:hi], non_blocking=True)
+                else:
+                    x = self.h_x.to(dev, non_blocking=True)
             for k_, p_ in self.model.state_dict().items():
-                p_.copy_(self.h_sd[k_], non_blocking=True)
+                if part and k_ == "emb.weight":
+                    p_[lo:hi].copy_(self.h_sd[k_][lo:hi], non_blocking=True)
+                else:
+                    p_.copy_(self.h_sd[k_], non_blocking=True)
         torch.cuda.current_stream().wait_stream(self.copy_stream)
         return adj, x
 
@@ -441,7 +466,7 @@ def measure(wl: Workload, steps: int, warmup: int, rank: int, world: int, e2e_st
     out_host = [torch.empty((wl.k, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
 
     def e2e_step():
-        a, xx = wl.upload()
+        a, xx = wl.upload(shard=True)
         res = wl.step(a, xx)
         for o, r in zip(out_host, res):
             o[: r.shape[0]].copy_(r, non_blocking=True)
@@ -464,10 +489,13 @@ def measure(wl: Workload, steps: int, warmup: int, rank: int, world: int, e2e_st
         if world > 1:
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         e2e = {"value": total_pairs * e2e_steps / (float(tm.item()) * 1e-3), "unit": "pairs/s",
-               "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": 2 * wl.k * 12, "steps": e2e_steps,
+               "h2d_bytes_per_step": wl.h2d_bytes_sharded, "d2h_bytes_per_step": 2 * wl.k * 12, "steps": e2e_steps,
                "ms_per_step": float(tm.item()) / e2e_steps,
                "note": "per step and per rank: pinned-host graph + features + weights -> device, the product call, "
-                       "both [k,3] lists -> pinned host"}
+                       "both [k,3] lists -> pinned host" +
+                       ("; N > 1: every rank uploads the whole graph and the dense weights but only its row shard of the "
+                        "node features and of the embedding table (the rows its share of the row-sharded GNN reads)"
+                        if world > 1 else "")}
     return dict(ms_step=ms_step, total_pairs=total_pairs, phase_ms=phase_ms, stats=all_stats[-1], launches=launches,
                 spmm_ms=spmm_ms, e2e=e2e, outs=outs, adj=adj, x=x)
 
