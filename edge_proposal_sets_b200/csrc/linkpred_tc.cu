@@ -45,8 +45,8 @@ constexpr int P_MAX_RING = 10;                                     // first-laye
 constexpr int P_VROWS = 4;                                         // distinct owners of a 128-row tile whose h[v] row is staged
 constexpr int P_MAX_CHUNKS = 8;                                    // 32-column K-chunks per layer at H = 256
 constexpr int P_GROUP_WARPS = 4;                                   // warps per producer group
-// Warp roles: EW epilogue warps (4, or 8 = two per TMEM lane quarter, see the epilogue), then the MMA warp,
-// the pair-id warp and NG producer groups of four warps each.
+// Warp roles: 4 epilogue warps (one per TMEM lane quarter), then the MMA warp, the pair-id warp, NL loader warps
+// (fp16-table path) and NG producer groups of four warps each.
 // one CTA per SM: the whole register file is there to be used
 // (16384 registers per SM sub-partition, warps dealt round-robin: 18 warps -> 5 on one -> 96; 14 -> 4 -> 128)
 constexpr int P_EPI_WARPS = 4;                                     // one per TMEM lane quarter
@@ -609,7 +609,7 @@ linkpred_tc3_kernel(const void *__restrict__ h, const int *__restrict__ pu, cons
     // stream of this CTA's tiles (a chunk = 128 rows x 32 K) in ring stage (chunk % ring).
     // Lane mapping inside a group (128 threads): 4 consecutive lanes cover one row's chunk, each lane
     // 8 K-elements = one 16-byte unit of the swizzled stage; a warp instruction covers 8 rows.
-    //   fp16 table (the hot path): the h[u] pieces are ALREADY in the stage (TMA gather4, see the ids warp); the
+    //   fp16 table (the hot path): the h[u] pieces are ALREADY in the stage (cp.async, see the loader warps); the
     //       group multiplies them in place by h[v] — one 16-byte piece per thread and chunk, because the list is
     //       grouped by v (a row whose v differs fetches its own piece, predicated) — and hands the stage to the MMA;
     //   fp32 source (short pair lists, no table): 4 x LDG.128 per row into registers, rounded like the table.
